@@ -1,0 +1,121 @@
+// ionization_b200 -- shared device helpers (sm_100a, FP64 complex arithmetic, warp/CTA affine scans)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef double2 cplx;  // (re, im) -- same memory layout as numpy complex128 / C99 double complex
+
+#define ION_DEVINL __device__ __forceinline__
+
+ION_DEVINL cplx c_make(double re, double im) { return make_double2(re, im); }
+ION_DEVINL cplx c_zero() { return make_double2(0.0, 0.0); }
+ION_DEVINL cplx c_add(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+ION_DEVINL cplx c_sub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+ION_DEVINL cplx c_scale(cplx a, double s) { return make_double2(a.x * s, a.y * s); }
+ION_DEVINL cplx c_mul(cplx a, cplx b) { return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x)); }
+// a*b + c
+ION_DEVINL cplx c_fma(cplx a, cplx b, cplx c)
+{
+    return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
+}
+ION_DEVINL cplx c_conj(cplx a) { return make_double2(a.x, -a.y); }
+ION_DEVINL double c_abs2(cplx a) { return fma(a.x, a.x, a.y * a.y); }
+// 1 / a  (Smith-free: |a| is O(1) for Crank-Nicolson pivots; plain formula, as numpy's would round)
+ION_DEVINL cplx c_inv(cplx a)
+{
+    double d = 1.0 / c_abs2(a);
+    return make_double2(a.x * d, -a.y * d);
+}
+
+ION_DEVINL cplx shfl_up_c(cplx v, int d)
+{
+    return make_double2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
+}
+ION_DEVINL cplx shfl_down_c(cplx v, int d)
+{
+    return make_double2(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d));
+}
+ION_DEVINL cplx shfl_c(cplx v, int src)
+{
+    return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
+// 128-bit global accesses of one complex128
+ION_DEVINL cplx ld_c(const cplx *p) { return *p; }
+ION_DEVINL void st_c(cplx *p, cplx v) { *p = v; }
+
+// ---------------------------------------------------------------------------------------------
+// Affine-map scans.  Thread t carries the map f_t(v) = P_t * v + B_t.
+// FWD:  value entering thread t is (f_{t-1} o ... o f_0)(0)
+// !FWD: value entering thread t is (f_{t+1} o ... o f_{T-1})(0)        (reverse direction)
+// Kogge-Stone over the 32 lanes with shuffles, then over the <= 32 warp aggregates through
+// shared memory (every warp redoes the tiny second-level scan, so one __syncthreads suffices).
+// ---------------------------------------------------------------------------------------------
+template <bool FWD>
+ION_DEVINL void affine_scan_warp(cplx &P, cplx &B, int lane)
+{
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        cplx Pp = FWD ? shfl_up_c(P, s) : shfl_down_c(P, s);
+        cplx Bp = FWD ? shfl_up_c(B, s) : shfl_down_c(B, s);
+        bool act = FWD ? (lane >= s) : (lane + s < 32);
+        if (act) {
+            B = c_fma(P, Bp, B);
+            P = c_mul(P, Pp);
+        }
+    }
+}
+
+// smP/smB: 32 entries each, private to this call site (no reuse hazard inside one kernel phase).
+template <bool FWD>
+ION_DEVINL cplx affine_scan_block_exclusive(cplx P, cplx B, cplx *smP, cplx *smB, int tid, int nthreads)
+{
+    const int lane = tid & 31, warp = tid >> 5, nw = nthreads >> 5;
+    affine_scan_warp<FWD>(P, B, lane);
+    cplx win = c_zero();
+    if (nw > 1) {
+        if (lane == (FWD ? 31 : 0)) {
+            smP[warp] = P;
+            smB[warp] = B;
+        }
+        __syncthreads();
+        cplx wP = (lane < nw) ? smP[lane] : c_make(1.0, 0.0);
+        cplx wB = (lane < nw) ? smB[lane] : c_zero();
+        affine_scan_warp<FWD>(wP, wB, lane);
+        int src = FWD ? warp - 1 : warp + 1;
+        cplx v = shfl_c(wB, src & 31);
+        win = (src >= 0 && src < nw) ? v : c_zero();
+    }
+    // exclusive inside the warp
+    cplx Pe = FWD ? shfl_up_c(P, 1) : shfl_down_c(P, 1);
+    cplx Be = FWD ? shfl_up_c(B, 1) : shfl_down_c(B, 1);
+    bool first = FWD ? (lane == 0) : (lane == 31);
+    return first ? win : c_fma(Pe, win, Be);
+}
+
+// block-wide sum of NV doubles; result valid in thread 0.  sm: >= 32*NV doubles.
+template <int NV>
+ION_DEVINL void block_sum(double (&v)[NV], double *sm, int tid, int nthreads)
+{
+    const int lane = tid & 31, warp = tid >> 5, nw = (nthreads + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v[i] += __shfl_down_sync(0xffffffffu, v[i], s);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) sm[warp * NV + i] = v[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double x = (lane < nw) ? sm[lane * NV + i] : 0.0;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) x += __shfl_down_sync(0xffffffffu, x, s);
+            v[i] = x;
+        }
+    }
+    __syncthreads();
+}

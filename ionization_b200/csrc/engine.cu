@@ -1,0 +1,887 @@
+// ionization_b200 -- host side of the engine and the C-ABI (include/ionization_b200.h).
+//
+// One `ion_sim` = `batch` simulations on one mesh, wavefunction resident in HBM in the row-interleaved
+// layout of kernels.cuh.  ion_sim_step()/ion_sim_run() translate the reference's operator sequence
+// (evolution_methods.py:89-123, SURVEY.md App. C "operator order per step") into pair-local kernels:
+//
+//   length gauge   E_e E_o CN E_o E_e mask      ->  [ROT even(s_n [+ s_n+1])] [ROT-CN-ROT odd]            2 launches/step
+//   velocity gauge h1_e h1_o h2_ee h2_eo h2_oe h2_oo CN (reversed) mask
+//                                                ->  [ROT odd] [H2 even] [H2-CN-H2 odd] [H2 even rev] [ROT odd] [ROT even]
+//
+// Consecutive operators acting on the same l-pairs are fused into one kernel; the trailing even rotation
+// of step n, the mask and the leading even rotation of step n+1 commute with each other (all diagonal in r
+// on the same pair) and are fused across the step boundary whenever no observation is requested in between.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ionization_b200.h"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                              \
+    do {                                                                                                            \
+        cudaError_t _e = (expr);                                                                                    \
+        if (_e != cudaSuccess)                                                                                      \
+            return fail(ION_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" +         \
+                                       std::to_string(__LINE__) + ")");                                             \
+    } while (0)
+
+enum KernelKind : int {
+    KK_ROT = 0,
+    KK_ROT_CN_ROT,
+    KK_H2,
+    KK_H2_CN_H2,
+    KK_CN,
+    KK_LINE_SO_LEN,
+    KK_LINE_SO_VEL,
+    KK_LINE_CN,
+    KK_SWEEP_FLAT,
+    KK_MASK,
+    KK_OBSERVE,
+    KK_COUNT
+};
+const char *const kKernelNames[KK_COUNT] = {"rot",        "rot_cn_rot", "h2",        "h2_cn_h2", "cn",     "line_so_len",
+                                            "line_so_vel", "line_cn",    "sweep_flat", "mask",    "observe"};
+
+template <typename T>
+int dev_alloc(T **p, size_t n)
+{
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    if (n == 0) return ION_OK;
+    CUDA_TRY(cudaMalloc((void **)p, n * sizeof(T)));
+    return ION_OK;
+}
+
+}  // namespace
+
+
+
+struct ion_sim {
+    int program = 0;
+    int L = 0, R = 0, batch = 0, device = 0, L_total = 0, l_begin = 0;
+    int M = 4, T = 0, Rp = 0, tmax = 0;
+    bool line = false;
+    cudaStream_t stream = 0;
+
+    cplx *psi = nullptr, *io_stage = nullptr;
+    cplx *h_diag = nullptr;
+    double *h_off = nullptr;
+    std::vector<double> h_off_host;
+    cplx *w = nullptr, *aggP = nullptr, *aggQ = nullptr;
+    double *toff = nullptr, *toff_prev = nullptr;
+    double *vec = nullptr, *zvec = nullptr, *zprev = nullptr, *mask = nullptr, *rvec = nullptr;
+    double *cl = nullptr, *cl2 = nullptr, *cl_z = nullptr;
+    double *scal = nullptr;
+    size_t scal_cap = 0;
+
+    double ipm = 1.0;
+    int n_states = 0, n_radii = 0;
+    double radii[ION_MAX_RADII] = {0};
+    cplx *state_rows = nullptr;
+    int *state_first = nullptr, *state_order = nullptr;
+    double *partial = nullptr, *ip_out = nullptr, *obs_out = nullptr;
+    size_t obs_cap = 0;
+
+    bool have_h = false, have_coupling = false;
+    double factored_tau = 0.0;
+    bool factored = false;
+    int64_t launch_count = 0;
+
+    // profiling
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> ev_kind;
+
+    ~ion_sim()
+    {
+        cudaSetDevice(device);
+        void *ptrs[] = {psi,  io_stage, h_diag, h_off, w,    aggP, aggQ,       toff,        toff_prev,   vec,     zvec,   zprev,
+                        mask, rvec,     cl,     cl2,   cl_z, scal, state_rows, state_first, state_order, partial, ip_out, obs_out};
+        for (void *p : ptrs)
+            if (p) cudaFree(p);
+        for (auto e : ev) cudaEventDestroy(e);
+    }
+};
+
+namespace {
+
+// host vector [R] -> device, permuted to [M][T], zero padded; rows >= limit are zeroed
+int upload_permuted(ion_sim *s, const double *src, int n_valid, double **dst, double **dst_prev)
+{
+    std::vector<double> tmp((size_t)s->Rp, 0.0), prev((size_t)s->T, 0.0);
+    for (int i = 0; i < n_valid; ++i) tmp[(size_t)(i % s->M) * s->T + (i / s->M)] = src[i];
+    if (dst_prev)
+        for (int t = 1; t < s->T; ++t) {
+            int i = t * s->M - 1;
+            prev[t] = i < n_valid ? src[i] : 0.0;
+        }
+    if (int rc = dev_alloc(dst, (size_t)s->Rp)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(*dst, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (dst_prev) {
+        if (int rc = dev_alloc(dst_prev, (size_t)s->T)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(*dst_prev, prev.data(), prev.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return ION_OK;
+}
+
+int upload_plain(ion_sim *s, const double *src, size_t n, double **dst)
+{
+    if (int rc = dev_alloc(dst, n)) return rc;
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    }
+    return ION_OK;
+}
+
+void prof_begin(ion_sim *s, int kind)
+{
+    if (!s->profiling) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s->stream);
+    s->ev.push_back(e);
+    s->ev_kind.push_back(kind);
+}
+void prof_end(ion_sim *s)
+{
+    if (!s->profiling) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s->stream);
+    s->ev.push_back(e);
+    s->ev_kind.push_back(-1);
+}
+
+size_t unit_smem_bytes(const ion_sim *s) { return (256 + 4 * (size_t)s->T) * sizeof(cplx); }
+
+template <int PROG>
+int launch_unit_prog(ion_sim *s, const ion::UnitParams &p, dim3 grid)
+{
+    const size_t smem = unit_smem_bytes(s);
+    const dim3 block(s->T);
+#define ION_LAUNCH(TMAX)                                                                                            \
+    do {                                                                                                            \
+        auto kern = ion::k_unit<4, PROG, TMAX>;                                                                     \
+        if (smem > 48 * 1024) {                                                                                     \
+            static bool attr_set[64] = {false};                                                                     \
+            if (!attr_set[s->device & 63]) {                                                                        \
+                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));       \
+                attr_set[s->device & 63] = true;                                                                    \
+            }                                                                                                       \
+        }                                                                                                           \
+        kern<<<grid, block, smem, s->stream>>>(p);                                                                  \
+    } while (0)
+    if (s->tmax == 256) ION_LAUNCH(256);
+    else if (s->tmax == 512) ION_LAUNCH(512);
+    else ION_LAUNCH(1024);
+#undef ION_LAUNCH
+    CUDA_TRY(cudaGetLastError());
+    return ION_OK;
+}
+
+ion::UnitParams base_params(ion_sim *s)
+{
+    ion::UnitParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.psi = s->psi;
+    p.w = s->w;
+    p.aggP = s->aggP;
+    p.aggQ = s->aggQ;
+    p.toff = s->toff;
+    p.toff_prev = s->toff_prev;
+    p.vec = s->vec;
+    p.zvec = s->zvec;
+    p.zprev = s->zprev;
+    p.mask = s->mask;
+    p.cl = s->cl;
+    p.cl2 = s->cl2;
+    p.L = s->L;
+    p.T = s->T;
+    p.l_begin = s->l_begin;
+    return p;
+}
+
+int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, const double *sb)
+{
+    ion::UnitParams p = base_params(s);
+    p.parity = parity;
+    p.flags = flags;
+    if ((flags & ion::F_MASK) && !s->mask) p.flags &= ~ion::F_MASK;
+    p.scal_a = sa;
+    p.scal_b = sb;
+    int units;
+    int kind;
+    switch (prog) {
+        case ion::PROG_CN:
+        case ion::PROG_LINE_SO_LEN:
+        case ion::PROG_LINE_SO_VEL: units = s->L; break;
+        default: units = ion::num_units(s->L, s->l_begin, parity);
+    }
+    dim3 grid(units, s->batch);
+    int rc = ION_OK;
+    switch (prog) {
+        case ion::PROG_ROT:
+            kind = KK_ROT;
+            prof_begin(s, kind);
+            rc = launch_unit_prog<ion::PROG_ROT>(s, p, grid);
+            break;
+        case ion::PROG_ROT_CN_ROT:
+            kind = KK_ROT_CN_ROT;
+            prof_begin(s, kind);
+            rc = launch_unit_prog<ion::PROG_ROT_CN_ROT>(s, p, grid);
+            break;
+        case ion::PROG_H2:
+            kind = KK_H2;
+            prof_begin(s, kind);
+            rc = launch_unit_prog<ion::PROG_H2>(s, p, grid);
+            break;
+        case ion::PROG_H2_CN_H2:
+            kind = KK_H2_CN_H2;
+            prof_begin(s, kind);
+            rc = launch_unit_prog<ion::PROG_H2_CN_H2>(s, p, grid);
+            break;
+        case ion::PROG_CN:
+            kind = KK_CN;
+            prof_begin(s, kind);
+            rc = launch_unit_prog<ion::PROG_CN>(s, p, grid);
+            break;
+        case ion::PROG_LINE_SO_LEN:
+            kind = KK_LINE_SO_LEN;
+            prof_begin(s, kind);
+            rc = launch_unit_prog<ion::PROG_LINE_SO_LEN>(s, p, grid);
+            break;
+        case ion::PROG_LINE_SO_VEL:
+            kind = KK_LINE_SO_VEL;
+            prof_begin(s, kind);
+            rc = launch_unit_prog<ion::PROG_LINE_SO_VEL>(s, p, grid);
+            break;
+        default: return fail(ION_EINVAL, "unknown unit program");
+    }
+    prof_end(s);
+    s->launch_count++;
+    return rc;
+}
+
+int launch_sweep_flat(ion_sim *s, int parity, int flags, const double *sa)
+{
+    if (s->L < 2) return ION_OK;
+    ion::SweepParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.psi = s->psi;
+    p.vec = s->vec;
+    p.cl = s->cl;
+    p.scal_a = sa;
+    p.L = s->L;
+    p.L_total = s->L_total;
+    p.l_begin = s->l_begin;
+    p.T = s->T;
+    p.M = s->M;
+    p.R = s->R;
+    p.parity = parity;
+    p.flags = flags;
+    dim3 block(128), grid((s->Rp + 127) / 128, s->L - 1, s->batch);
+    prof_begin(s, KK_SWEEP_FLAT);
+    ion::k_sweep_flat<<<grid, block, 0, s->stream>>>(p);
+    prof_end(s);
+    s->launch_count++;
+    CUDA_TRY(cudaGetLastError());
+    return ION_OK;
+}
+
+int launch_mask(ion_sim *s)
+{
+    if (!s->mask) return ION_OK;
+    long long n = (long long)s->batch * s->L;
+    dim3 block(128), grid((s->Rp + 127) / 128, (unsigned)std::min<long long>(n, 4096));
+    prof_begin(s, KK_MASK);
+    ion::k_mask<<<grid, block, 0, s->stream>>>(s->psi, s->mask, s->Rp, n);
+    prof_end(s);
+    s->launch_count++;
+    CUDA_TRY(cudaGetLastError());
+    return ION_OK;
+}
+
+// (re)build the LU factors of (1 + i tau H0) when tau changed
+int ensure_factor(ion_sim *s, double tau)
+{
+    if (s->factored && std::fabs(tau - s->factored_tau) <= 1e-9 * std::fabs(tau)) return ION_OK;
+    if (!s->have_h) return fail(ION_ESTATE, "ion_sim_set_hamiltonian must be called before stepping");
+    // toff (host-side, tiny)
+    std::vector<double> off(s->h_off_host);
+    for (auto &v : off) v *= tau;
+    if (int rc = upload_permuted(s, off.data(), s->R - 1, &s->toff, &s->toff_prev)) return rc;
+    if (int rc = dev_alloc(&s->w, (size_t)s->L * s->Rp)) return rc;
+    if (int rc = dev_alloc(&s->aggP, (size_t)s->L * s->T)) return rc;
+    if (int rc = dev_alloc(&s->aggQ, (size_t)s->L * s->T)) return rc;
+    ion::k_factor<<<(s->L + 31) / 32, 32, 0, s->stream>>>(s->h_diag, s->h_off, tau, s->L, s->R, s->M, s->T, s->w);
+    CUDA_TRY(cudaGetLastError());
+    dim3 g2((s->T + 127) / 128, s->L);
+    ion::k_aggregates<<<g2, 128, 0, s->stream>>>(s->w, s->toff, s->L, s->M, s->T, s->aggP, s->aggQ);
+    CUDA_TRY(cudaGetLastError());
+    s->factored = true;
+    s->factored_tau = tau;
+    return ION_OK;
+}
+
+bool fast_l_path(const ion_sim *s) { return (s->L_total % 2) == 0; }
+
+// one step; `pre_done`: the leading even rotation of this step was already fused into the previous step's tail;
+// `fuse_next`: fold the leading even rotation of the next step into this step's tail.
+int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, bool pre_done, bool fuse_next)
+{
+    using namespace ion;
+    int rc = ION_OK;
+    switch (s->program) {
+        case ION_SH_LEN_SO:
+            if (fast_l_path(s)) {
+                if (!pre_done && (rc = launch_unit(s, PROG_ROT, 0, 0, sa, nullptr))) return rc;
+                if ((rc = launch_unit(s, PROG_ROT_CN_ROT, 1, 0, sa, nullptr))) return rc;
+                return launch_unit(s, PROG_ROT, 0, F_MASK, sa, fuse_next ? sb_next : nullptr);
+            }
+            if ((rc = launch_sweep_flat(s, 0, 0, sa))) return rc;
+            if ((rc = launch_sweep_flat(s, 1, 0, sa))) return rc;
+            if ((rc = launch_unit(s, PROG_CN, 0, 0, nullptr, nullptr))) return rc;
+            if ((rc = launch_sweep_flat(s, 1, 0, sa))) return rc;
+            if ((rc = launch_sweep_flat(s, 0, 0, sa))) return rc;
+            return launch_mask(s);
+        case ION_SH_VEL_SO: {
+            const bool fast = fast_l_path(s);
+            if (fast) {
+                if (!pre_done && (rc = launch_unit(s, PROG_ROT, 0, F_REAL_ROT, sa, nullptr))) return rc;
+                if ((rc = launch_unit(s, PROG_ROT, 1, F_REAL_ROT, sa, nullptr))) return rc;
+            } else {
+                if ((rc = launch_sweep_flat(s, 0, F_REAL_ROT, sa))) return rc;
+                if ((rc = launch_sweep_flat(s, 1, F_REAL_ROT, sa))) return rc;
+            }
+            if ((rc = launch_unit(s, PROG_H2, 0, 0, sa, nullptr))) return rc;              // ee, eo
+            if ((rc = launch_unit(s, PROG_H2_CN_H2, 1, 0, sa, nullptr))) return rc;        // oe, oo, CN, oo, oe
+            if ((rc = launch_unit(s, PROG_H2, 0, F_H2_REVERSE, sa, nullptr))) return rc;   // eo, ee
+            if (fast) {
+                if ((rc = launch_unit(s, PROG_ROT, 1, F_REAL_ROT, sa, nullptr))) return rc;
+                return launch_unit(s, PROG_ROT, 0, F_REAL_ROT | F_MASK, sa, fuse_next ? sb_next : nullptr);
+            }
+            if ((rc = launch_sweep_flat(s, 1, F_REAL_ROT, sa))) return rc;
+            if ((rc = launch_sweep_flat(s, 0, F_REAL_ROT, sa))) return rc;
+            return launch_mask(s);
+        }
+        case ION_LINE_LEN_SO: return launch_unit(s, PROG_LINE_SO_LEN, 0, F_MASK, sa, nullptr);
+        case ION_LINE_VEL_SO: return launch_unit(s, PROG_LINE_SO_VEL, 0, F_MASK, sa, nullptr);
+        default: return fail(ION_ENOTSUP, "program not supported by this build");
+    }
+}
+
+bool program_fuses(const ion_sim *s)
+{
+    return (s->program == ION_SH_LEN_SO || s->program == ION_SH_VEL_SO) && fast_l_path(s);
+}
+
+int check_ready(ion_sim *s)
+{
+    if (!s->have_h) return fail(ION_ESTATE, "ion_sim_set_hamiltonian must be called before stepping");
+    if (!s->have_coupling) return fail(ION_ESTATE, "the coupling vectors of this program have not been set");
+    return ION_OK;
+}
+
+int upload_scalars(ion_sim *s, int64_t n_steps, const double *taus, const double *fields)
+{
+    size_t need = (size_t)(n_steps + 1) * s->batch;
+    if (need > s->scal_cap) {
+        if (int rc = dev_alloc(&s->scal, need)) return rc;
+        s->scal_cap = need;
+    }
+    std::vector<double> h(need, 0.0);
+    for (int64_t n = 0; n < n_steps; ++n)
+        for (int b = 0; b < s->batch; ++b) h[(size_t)n * s->batch + b] = taus[n] * fields[(size_t)n * s->batch + b];
+    CUDA_TRY(cudaMemcpyAsync(s->scal, h.data(), need * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));  // h goes out of scope
+    return ION_OK;
+}
+
+int launch_observe(ion_sim *s, uint32_t what, double *dev_out)
+{
+    ion::ObserveParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.psi = s->psi;
+    p.rvec = s->rvec;
+    p.h_diag = s->h_diag;
+    p.h_off = s->h_off;
+    p.cl_z = s->cl_z;
+    p.state_rows = s->state_rows;
+    p.state_first = s->state_first;
+    p.state_order = s->state_order;
+    p.partial = s->partial;
+    p.ip_out = s->ip_out;
+    for (int q = 0; q < s->n_radii; ++q) p.radii[q] = s->radii[q];
+    p.n_radii = (what & ION_OBS_NORM_WITHIN) ? s->n_radii : 0;
+    p.n_states = (what & ION_OBS_INNER_PRODUCTS) ? s->n_states : 0;
+    p.L = s->L;
+    p.L_total = s->L_total;
+    p.l_begin = s->l_begin;
+    p.R = s->R;
+    p.M = s->M;
+    p.T = s->T;
+    p.what = what;
+    p.ipm = s->ipm;
+    p.line = s->line ? 1 : 0;
+    prof_begin(s, KK_OBSERVE);
+    ion::k_observe<<<dim3(s->L, s->batch), 256, 0, s->stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    long long rec = ion_sim_observation_size(s, what);
+    ion::k_observe_finish<<<(s->batch + 63) / 64, 64, 0, s->stream>>>(s->partial, s->ip_out, dev_out, s->batch, s->L, p.n_states,
+                                                                     p.n_radii, what, s->ipm, rec);
+    prof_end(s);
+    s->launch_count += 2;
+    CUDA_TRY(cudaGetLastError());
+    return ION_OK;
+}
+
+int ensure_observe_buffers(ion_sim *s, size_t n_records, uint32_t what)
+{
+    if (!s->partial) {
+        if (int rc = dev_alloc(&s->partial, (size_t)s->batch * s->L * (4 + ION_MAX_RADII))) return rc;
+    }
+    if (!s->ip_out) {
+        if (int rc = dev_alloc(&s->ip_out, (size_t)s->batch * std::max(s->n_states, 1) * 2)) return rc;
+    }
+    size_t need = n_records * s->batch * (size_t)ion_sim_observation_size(s, what);
+    if (need > s->obs_cap) {
+        if (int rc = dev_alloc(&s->obs_out, need)) return rc;
+        s->obs_cap = need;
+    }
+    return ION_OK;
+}
+
+int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fields, const uint8_t *observe_mask, uint32_t what,
+             double *out)
+{
+    if (n_steps < 0) return fail(ION_EINVAL, "n_steps < 0");
+    if (n_steps == 0) return ION_OK;
+    if (!taus || !fields) return fail(ION_EINVAL, "taus/fields must not be NULL");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (int rc = check_ready(s)) return rc;
+    int64_t n_obs = 0;
+    if (observe_mask)
+        for (int64_t n = 0; n < n_steps; ++n) n_obs += observe_mask[n] ? 1 : 0;
+    if (n_obs && !out) return fail(ION_EINVAL, "out must not be NULL when observations are requested");
+    if (n_obs)
+        if (int rc = ensure_observe_buffers(s, (size_t)n_obs, what)) return rc;
+    if (int rc = upload_scalars(s, n_steps, taus, fields)) return rc;
+    const size_t rec = (size_t)ion_sim_observation_size(s, what) * s->batch;
+    const bool can_fuse = program_fuses(s);
+    bool pre_done = false;
+    int64_t k_obs = 0;
+    for (int64_t n = 0; n < n_steps; ++n) {
+        if (int rc = ensure_factor(s, taus[n])) return rc;
+        const bool obs = observe_mask && observe_mask[n];
+        const bool fuse_next = can_fuse && (n + 1 < n_steps) && !obs;
+        const double *sa = s->scal + (size_t)n * s->batch;
+        if (int rc = enqueue_step(s, sa, sa + s->batch, pre_done, fuse_next)) return rc;
+        pre_done = fuse_next;
+        if (obs) {
+            if (int rc = launch_observe(s, what, s->obs_out + (size_t)k_obs * rec)) return rc;
+            ++k_obs;
+        }
+    }
+    if (n_obs) {
+        CUDA_TRY(cudaMemcpyAsync(out, s->obs_out, (size_t)n_obs * rec * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    }
+    return ION_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C-ABI
+// =============================================================================================
+extern "C" {
+
+int ion_abi_version(void) { return ION_ABI_VERSION; }
+const char *ion_last_error(void) { return g_last_error.c_str(); }
+
+int ion_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int ion_tdma_c128(const void *sub, const void *diag, const void *sup, const void *rhs, void *x, int64_t n, int64_t batch,
+                  int device)
+{
+    if (n < 1 || batch < 0) return fail(ION_EINVAL, "ion_tdma_c128: need n >= 1, batch >= 0");
+    if (batch == 0) return ION_OK;
+    if (!diag || !rhs || !x || (n > 1 && (!sub || !sup))) return fail(ION_EINVAL, "ion_tdma_c128: NULL array");
+    if (ion_device_count() <= device) return fail(ION_ENODEVICE, "ion_tdma_c128: no CUDA device " + std::to_string(device));
+    CUDA_TRY(cudaSetDevice(device));
+    cplx *d_sub = nullptr, *d_diag = nullptr, *d_sup = nullptr, *d_rhs = nullptr, *d_x = nullptr, *d_scratch = nullptr;
+    const size_t nb = (size_t)batch * n * sizeof(cplx), nb1 = (size_t)batch * (n - 1) * sizeof(cplx);
+    auto cleanup = [&]() {
+        cudaFree(d_sub), cudaFree(d_diag), cudaFree(d_sup), cudaFree(d_rhs), cudaFree(d_x), cudaFree(d_scratch);
+    };
+    int rc = ION_OK;
+    do {
+        if ((rc = dev_alloc(&d_diag, (size_t)batch * n)) || (rc = dev_alloc(&d_rhs, (size_t)batch * n)) ||
+            (rc = dev_alloc(&d_x, (size_t)batch * n)) || (rc = dev_alloc(&d_sub, (size_t)batch * std::max<int64_t>(n - 1, 1))) ||
+            (rc = dev_alloc(&d_sup, (size_t)batch * std::max<int64_t>(n - 1, 1))))
+            break;
+        cudaError_t e = cudaSuccess;
+        if (n > 1) {
+            e = cudaMemcpy(d_sub, sub, nb1, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(d_sup, sup, nb1, cudaMemcpyHostToDevice);
+        }
+        if (e == cudaSuccess) e = cudaMemcpy(d_diag, diag, nb, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_rhs, rhs, nb, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            rc = fail(ION_ECUDA, std::string("ion_tdma_c128 H2D: ") + cudaGetErrorString(e));
+            break;
+        }
+        size_t smem = 2 * (size_t)n * sizeof(cplx);
+        if (smem > 160 * 1024) {
+            if ((rc = dev_alloc(&d_scratch, (size_t)batch * 2 * n))) break;
+            smem = 0;
+        } else if (smem > 48 * 1024) {
+            e = cudaFuncSetAttribute(ion::k_tdma_general, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024);
+        }
+        if (e == cudaSuccess) {
+            ion::k_tdma_general<<<(unsigned)batch, 128, smem>>>(d_sub, d_diag, d_sup, d_rhs, d_x, n, d_scratch);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpy(x, d_x, nb, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(ION_ECUDA, std::string("ion_tdma_c128: ") + cudaGetErrorString(e));
+    } while (0);
+    cleanup();
+    return rc;
+}
+
+int ion_sim_create_sharded(int program, int64_t L_total, int64_t l_begin, int64_t L, int64_t R, int64_t batch, int device,
+                           ion_sim_t **out)
+{
+    if (!out) return fail(ION_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (L < 1 || R < 2 || batch < 1 || l_begin < 0 || l_begin + L > L_total)
+        return fail(ION_EINVAL, "need L >= 1, R >= 2, batch >= 1, 0 <= l_begin, l_begin + L <= L_total");
+    const bool line = (program == ION_LINE_LEN_CN || program == ION_LINE_LEN_SO || program == ION_LINE_VEL_SO);
+    if (program < 0 || program > ION_SH_LEN_ADI) return fail(ION_EINVAL, "unknown program");
+    if (line && L_total != 1) return fail(ION_EINVAL, "LineMesh programs need L = 1");
+    if (program == ION_SH_LEN_ADI) return fail(ION_ENOTSUP, "ION_SH_LEN_ADI is not implemented in this build");
+    if (program == ION_LINE_LEN_CN) return fail(ION_ENOTSUP, "ION_LINE_LEN_CN is not implemented in this build");
+    if (L != L_total) return fail(ION_ENOTSUP, "l-block sharding is not implemented in this build");
+    if (ion_device_count() <= device || device < 0)
+        return fail(ION_ENODEVICE, "no CUDA device " + std::to_string(device) + " (the engine has no CPU path)");
+    const int M = 4;
+    int64_t T = (R + M - 1) / M;
+    T = (T + 31) / 32 * 32;
+    if (T > 1024) return fail(ION_ENOTSUP, "r_points > 4096 is not supported by this build");
+    CUDA_TRY(cudaSetDevice(device));
+    ion_sim *s = new ion_sim();
+    s->program = program;
+    s->L = (int)L;
+    s->R = (int)R;
+    s->batch = (int)batch;
+    s->device = device;
+    s->L_total = (int)L_total;
+    s->l_begin = (int)l_begin;
+    s->M = M;
+    s->T = (int)T;
+    s->Rp = (int)(M * T);
+    s->tmax = T <= 256 ? 256 : (T <= 512 ? 512 : 1024);
+    s->line = line;
+    int rc = dev_alloc(&s->psi, (size_t)batch * L * s->Rp);
+    if (rc == ION_OK) {
+        cudaError_t e = cudaMemset(s->psi, 0, (size_t)batch * L * s->Rp * sizeof(cplx));
+        if (e != cudaSuccess) rc = fail(ION_ECUDA, cudaGetErrorString(e));
+    }
+    if (rc != ION_OK) {
+        delete s;
+        return rc;
+    }
+    *out = s;
+    return ION_OK;
+}
+
+int ion_sim_create(int program, int64_t L, int64_t R, int64_t batch, int device, ion_sim_t **out)
+{
+    return ion_sim_create_sharded(program, L, 0, L, R, batch, device, out);
+}
+
+int ion_sim_destroy(ion_sim_t *s)
+{
+    if (!s) return ION_OK;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    delete s;
+    return ION_OK;
+}
+
+int ion_sim_set_stream(ion_sim_t *s, void *cuda_stream)
+{
+    if (!s) return fail(ION_EINVAL, "sim is NULL");
+    s->stream = (cudaStream_t)cuda_stream;
+    return ION_OK;
+}
+
+int ion_sim_set_hamiltonian(ion_sim_t *s, const void *h_diag, const double *h_off)
+{
+    if (!s || !h_diag || !h_off) return fail(ION_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (int rc = dev_alloc(&s->h_diag, (size_t)s->L * s->R)) return rc;
+    if (int rc = dev_alloc(&s->h_off, (size_t)s->R - 1)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s->h_diag, h_diag, (size_t)s->L * s->R * sizeof(cplx), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->h_off, h_off, ((size_t)s->R - 1) * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->h_off_host.assign(h_off, h_off + (s->R - 1));
+    s->have_h = true;
+    s->factored = false;
+    return ION_OK;
+}
+
+int ion_sim_set_len_coupling(ion_sim_t *s, const double *c_l, const double *x_j)
+{
+    if (!s || !x_j || (s->L_total > 1 && !c_l)) return fail(ION_EINVAL, "NULL argument");
+    if (s->program != ION_SH_LEN_SO) return fail(ION_EINVAL, "length-gauge coupling does not belong to this program");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (int rc = upload_plain(s, c_l, (size_t)s->L_total - 1, &s->cl)) return rc;
+    if (int rc = upload_plain(s, c_l, (size_t)s->L_total - 1, &s->cl_z)) return rc;
+    if (int rc = upload_permuted(s, x_j, s->R, &s->vec, nullptr)) return rc;
+    s->have_coupling = true;
+    return ION_OK;
+}
+
+int ion_sim_set_vel_coupling(ion_sim_t *s, const double *c_l, const double *f1_l, const double *y_j, const double *z_j)
+{
+    if (!s || !y_j || !z_j || (s->L_total > 1 && (!c_l || !f1_l))) return fail(ION_EINVAL, "NULL argument");
+    if (s->program != ION_SH_VEL_SO) return fail(ION_EINVAL, "velocity-gauge coupling does not belong to this program");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (int rc = upload_plain(s, f1_l, (size_t)s->L_total - 1, &s->cl)) return rc;
+    if (int rc = upload_plain(s, c_l, (size_t)s->L_total - 1, &s->cl2)) return rc;
+    if (int rc = upload_plain(s, c_l, (size_t)s->L_total - 1, &s->cl_z)) return rc;
+    if (int rc = upload_permuted(s, y_j, s->R, &s->vec, nullptr)) return rc;
+    if (int rc = upload_permuted(s, z_j, s->R - 1, &s->zvec, &s->zprev)) return rc;
+    s->have_coupling = true;
+    return ION_OK;
+}
+
+int ion_sim_set_line_coupling(ion_sim_t *s, const double *w_z, double v_pref)
+{
+    if (!s) return fail(ION_EINVAL, "sim is NULL");
+    if (!s->line) return fail(ION_EINVAL, "line coupling does not belong to this program");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (s->program == ION_LINE_VEL_SO) {
+        std::vector<double> z((size_t)s->R - 1, v_pref);
+        if (int rc = upload_permuted(s, z.data(), s->R - 1, &s->zvec, &s->zprev)) return rc;
+    } else {
+        if (!w_z) return fail(ION_EINVAL, "w_z is NULL");
+        if (int rc = upload_permuted(s, w_z, s->R, &s->vec, nullptr)) return rc;
+    }
+    s->have_coupling = true;
+    return ION_OK;
+}
+
+int ion_sim_set_mask(ion_sim_t *s, const double *mask)
+{
+    if (!s) return fail(ION_EINVAL, "sim is NULL");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (!mask) {
+        if (s->mask) cudaFree(s->mask);
+        s->mask = nullptr;
+        return ION_OK;
+    }
+    return upload_permuted(s, mask, s->R, &s->mask, nullptr);
+}
+
+int ion_sim_set_observables(ion_sim_t *s, double ipm, const double *r_j, int64_t n_states, const int64_t *state_l,
+                            const void *state_rows, int64_t n_radii, const double *radii)
+{
+    if (!s) return fail(ION_EINVAL, "sim is NULL");
+    if (n_radii > ION_MAX_RADII) return fail(ION_ENOTSUP, "at most 8 radii");
+    if (n_states < 0 || n_radii < 0 || (n_states > 0 && (!state_l || !state_rows)) || (n_radii > 0 && !radii))
+        return fail(ION_EINVAL, "inconsistent observables arguments");
+    CUDA_TRY(cudaSetDevice(s->device));
+    s->ipm = ipm;
+    if (r_j) {
+        if (int rc = upload_permuted(s, r_j, s->R, &s->rvec, nullptr)) return rc;
+    }
+    s->n_radii = (int)n_radii;
+    for (int q = 0; q < n_radii; ++q) s->radii[q] = radii[q];
+    // test states owned by this shard, grouped by channel (CSR)
+    s->n_states = (int)n_states;
+    if (s->ip_out) {
+        cudaFree(s->ip_out);
+        s->ip_out = nullptr;
+    }
+    std::vector<int> first((size_t)s->L + 1, 0), order;
+    for (int l = 0; l < s->L; ++l) {
+        first[l] = (int)order.size();
+        for (int64_t k = 0; k < n_states; ++k)
+            if (state_l[k] == s->l_begin + l) order.push_back((int)k);
+    }
+    first[s->L] = (int)order.size();
+    for (int64_t k = 0; k < n_states; ++k)
+        if (state_l[k] < 0 || state_l[k] >= s->L_total) return fail(ION_EINVAL, "state_l out of range");
+    if (int rc = dev_alloc(&s->state_first, first.size())) return rc;
+    CUDA_TRY(cudaMemcpy(s->state_first, first.data(), first.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (int rc = dev_alloc(&s->state_order, std::max<size_t>(order.size(), 1))) return rc;
+    if (!order.empty())
+        CUDA_TRY(cudaMemcpy(s->state_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (n_states > 0) {
+        cplx *stage = nullptr;
+        if (int rc = dev_alloc(&stage, (size_t)n_states * s->R)) return rc;
+        if (int rc = dev_alloc(&s->state_rows, (size_t)n_states * s->Rp)) {
+            cudaFree(stage);
+            return rc;
+        }
+        cudaError_t e = cudaMemcpy(stage, state_rows, (size_t)n_states * s->R * sizeof(cplx), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            dim3 grid((s->Rp + 127) / 128, (unsigned)std::min<int64_t>(n_states, 4096));
+            ion::k_to_internal_c<<<grid, 128, 0, s->stream>>>(stage, s->state_rows, s->R, s->M, s->T, n_states);
+            e = cudaStreamSynchronize(s->stream);
+        }
+        cudaFree(stage);
+        if (e != cudaSuccess) return fail(ION_ECUDA, cudaGetErrorString(e));
+    }
+    return ION_OK;
+}
+
+int ion_sim_write_g(ion_sim_t *s, const void *g)
+{
+    if (!s || !g) return fail(ION_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const size_t n = (size_t)s->batch * s->L;
+    if (!s->io_stage)
+        if (int rc = dev_alloc(&s->io_stage, n * s->R)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s->io_stage, g, n * s->R * sizeof(cplx), cudaMemcpyHostToDevice, s->stream));
+    dim3 grid((s->Rp + 127) / 128, (unsigned)std::min<size_t>(n, 8192));
+    ion::k_to_internal_c<<<grid, 128, 0, s->stream>>>(s->io_stage, s->psi, s->R, s->M, s->T, (long long)n);
+    s->launch_count++;
+    CUDA_TRY(cudaGetLastError());
+    return ION_OK;
+}
+
+int ion_sim_read_g(ion_sim_t *s, void *g)
+{
+    if (!s || !g) return fail(ION_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const size_t n = (size_t)s->batch * s->L;
+    if (!s->io_stage)
+        if (int rc = dev_alloc(&s->io_stage, n * s->R)) return rc;
+    dim3 grid((s->Rp + 127) / 128, (unsigned)std::min<size_t>(n, 8192));
+    ion::k_from_internal_c<<<grid, 128, 0, s->stream>>>(s->psi, s->io_stage, s->R, s->M, s->T, (long long)n);
+    s->launch_count++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(g, s->io_stage, n * s->R * sizeof(cplx), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return ION_OK;
+}
+
+int ion_sim_step(ion_sim_t *s, int64_t n_steps, const double *taus, const double *fields)
+{
+    if (!s) return fail(ION_EINVAL, "sim is NULL");
+    return run_impl(s, n_steps, taus, fields, nullptr, 0, nullptr);
+}
+
+int64_t ion_sim_observation_size(ion_sim_t *s, uint32_t what)
+{
+    if (!s) return 0;
+    int64_t n = 0;
+    if (what & ION_OBS_NORM) n += 1;
+    if (what & ION_OBS_INNER_PRODUCTS) n += 2 * (int64_t)s->n_states;
+    if (what & ION_OBS_NORM_BY_L) n += s->L;
+    if (what & ION_OBS_R) n += 1;
+    if (what & ION_OBS_Z) n += 1;
+    if (what & ION_OBS_H0) n += 1;
+    if (what & ION_OBS_NORM_WITHIN) n += s->n_radii;
+    return n;
+}
+
+int ion_sim_observe(ion_sim_t *s, uint32_t what, double *out)
+{
+    if (!s || !out) return fail(ION_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (int rc = ensure_observe_buffers(s, 1, what)) return rc;
+    if (int rc = launch_observe(s, what, s->obs_out)) return rc;
+    const size_t rec = (size_t)ion_sim_observation_size(s, what) * s->batch;
+    CUDA_TRY(cudaMemcpyAsync(out, s->obs_out, rec * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return ION_OK;
+}
+
+int ion_sim_run(ion_sim_t *s, int64_t n_steps, const double *taus, const double *fields, const uint8_t *observe_mask,
+                uint32_t what, double *out)
+{
+    if (!s) return fail(ION_EINVAL, "sim is NULL");
+    int rc = run_impl(s, n_steps, taus, fields, observe_mask, what, out);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return ION_OK;
+}
+
+int ion_sim_synchronize(ion_sim_t *s)
+{
+    if (!s) return fail(ION_EINVAL, "sim is NULL");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return ION_OK;
+}
+
+int ion_sim_halo_buffer(ion_sim_t *, int, void **, int64_t *) { return fail(ION_ENOTSUP, "l-block sharding is not implemented in this build"); }
+int ion_sim_num_phases(ion_sim_t *) { return 1; }
+int ion_sim_step_phase(ion_sim_t *, int, double, const double *) { return fail(ION_ENOTSUP, "l-block sharding is not implemented in this build"); }
+
+int ion_sim_device_psi(ion_sim_t *s, void **device_ptr, int64_t *n_bytes)
+{
+    if (!s || !device_ptr || !n_bytes) return fail(ION_EINVAL, "NULL argument");
+    *device_ptr = s->psi;
+    *n_bytes = (int64_t)((size_t)s->batch * s->L * s->Rp * sizeof(cplx));
+    return ION_OK;
+}
+
+int64_t ion_sim_launch_count(ion_sim_t *s) { return s ? s->launch_count : 0; }
+int ion_num_kernel_kinds(void) { return KK_COUNT; }
+const char *ion_kernel_name(int kind) { return (kind >= 0 && kind < KK_COUNT) ? kKernelNames[kind] : ""; }
+
+int ion_sim_profile(ion_sim_t *s, int64_t n_steps, const double *taus, const double *fields, double *ms, int64_t *launches)
+{
+    if (!s || !ms || !launches) return fail(ION_EINVAL, "NULL argument");
+    for (int k = 0; k < KK_COUNT; ++k) ms[k] = 0.0, launches[k] = 0;
+    s->profiling = true;
+    int rc = run_impl(s, n_steps, taus, fields, nullptr, 0, nullptr);
+    s->profiling = false;
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    if (rc == ION_OK && e == cudaSuccess) {
+        for (size_t i = 0; i + 1 < s->ev.size(); i += 2) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, s->ev[i], s->ev[i + 1]);
+            int k = s->ev_kind[i];
+            if (k >= 0 && k < KK_COUNT) ms[k] += t, launches[k]++;
+        }
+    }
+    for (auto ev : s->ev) cudaEventDestroy(ev);
+    s->ev.clear();
+    s->ev_kind.clear();
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(ION_ECUDA, cudaGetErrorString(e));
+    return ION_OK;
+}
+
+}  // extern "C"

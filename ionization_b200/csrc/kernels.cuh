@@ -1,0 +1,734 @@
+// ionization_b200 -- the hot-path kernels (sm_100a).
+//
+// DATA LAYOUT:  one l-channel of R radial points is owned by a CTA of T threads, thread t
+// holding the M CONSECUTIVE rows i = t*M + k, k = 0..M-1, in registers.  So that every global access is a
+// fully coalesced 128-bit access, each channel is stored "row-interleaved":
+//
+//        position(i) = (i % M) * T + (i / M)            i.e. psi[sim][l][k][t],  Rp = M*T >= R, zero padded.
+//
+// The same permutation is applied to every per-r coefficient vector, so kernels that are point-wise in r
+// never need to know it; kernels that couple r-neighbours (Crank-Nicolson, the velocity-gauge r-pair
+// rotations) find the neighbours i-1 / i+1 in the same thread, or in thread t-1 / t+1 at chunk edges.
+//
+// Every kernel works on "units": a unit is a pair of channels (l, l+1) with l % 2 == parity, or a single
+// left-over channel (l = 0 in odd sweeps, the last channel when it has no partner).  All the operators of the
+// reference's split-operator step are local to such a pair, so each kernel streams psi
+// through the SM exactly once: 128-bit loads -> registers -> 128-bit stores.
+#pragma once
+#include "common.cuh"
+
+namespace ion {
+
+enum : int {
+    F_MASK = 1,       // multiply by mask[r] at the end (mesh/meshes.py:257)
+    F_REAL_ROT = 2,   // rotation [[c, s], [-s, c]] (velocity gauge h1 / line) instead of [[c, -is], [-is, c]]
+    F_H2_REVERSE = 4, // r-sublayer order: default (r-even, r-odd); reversed (r-odd, r-even)
+};
+
+struct UnitParams {
+    cplx *psi;               // [batch][L][M][T]
+    const cplx *w;           // [L][M][T]   1/pivot of (1 + i tau H0), permuted      (k_factor)
+    const cplx *aggP;        // [L][T]      forward chunk multipliers
+    const cplx *aggQ;        // [L][T]      backward chunk multipliers
+    const double *toff;      // [M][T]      tau * h_off[i]   (0 for i >= R-1)
+    const double *toff_prev; // [T]         tau * h_off[t*M - 1] (0 for t = 0)
+    const double *vec;       // [M][T]      rotation coupling vector (x_j or y_j), 0 in the padding
+    const double *zvec;      // [M][T]      r-pair coupling z_j (0 for i >= R-1)
+    const double *zprev;     // [T]         z at row t*M - 1
+    const double *mask;      // [M][T] or nullptr
+    const double *cl;        // [L_total-1] l-pair coefficient for rotations (c_l or c_l*(l+1)), GLOBAL l
+    const double *cl2;       // [L_total-1] l-pair coefficient for the r-pair rotations
+    const double *scal_a;    // [batch] per-simulation scalar s = tau*field of this step (or nullptr = 0)
+    const double *scal_b;    // [batch] second scalar fused in (next step's), or nullptr
+    int L;                   // owned channels
+    int T;
+    int l_begin;             // global index of owned channel 0
+    int parity;              // parity (in GLOBAL l) of the lower channel of a pair
+    int flags;
+};
+
+// unit -> (first local channel, is pair).  Pairs are (l, l+1) with global l % 2 == parity.
+ION_DEVINL void unit_channels(const UnitParams &p, int unit, int &l0, bool &pair)
+{
+    // local parity of pair starts
+    int lp = (p.parity - (p.l_begin & 1)) & 1;
+    if (lp == 0) {
+        l0 = 2 * unit;
+    } else {
+        l0 = unit == 0 ? 0 : 2 * unit - 1;
+        if (unit == 0) {
+            pair = false;
+            return;
+        }
+    }
+    pair = (l0 + 1 < p.L);
+}
+inline int num_units(int L, int l_begin, int parity)
+{
+    int lp = (parity - (l_begin & 1)) & 1;
+    return lp == 0 ? (L + 1) / 2 : 1 + L / 2;
+}
+
+template <int M>
+ION_DEVINL void load_rows(cplx (&g)[M], const cplx *base, int T, int t)
+{
+#pragma unroll
+    for (int k = 0; k < M; ++k) g[k] = ld_c(base + k * T + t);
+}
+template <int M>
+ION_DEVINL void store_rows(const cplx (&g)[M], cplx *base, int T, int t)
+{
+#pragma unroll
+    for (int k = 0; k < M; ++k) st_c(base + k * T + t, g[k]);
+}
+template <int M>
+ION_DEVINL void load_vec(double (&v)[M], const double *base, int T, int t)
+{
+#pragma unroll
+    for (int k = 0; k < M; ++k) v[k] = base[k * T + t];
+}
+
+// ---------------------------------------------------------------------------------------------
+// l<->l+1 rotation of one pair, all rows of this thread.
+//   complex: [[cos a, -i sin a], [-i sin a, cos a]]   mesh_operators.py:1055-1075
+//   real:    [[cos a,  sin a], [-sin a,  cos a]]      mesh_operators.py:1204-1245
+// ---------------------------------------------------------------------------------------------
+template <int M, bool REAL>
+ION_DEVINL void rotate_pair(cplx (&A)[M], cplx (&B)[M], const double (&vec)[M], double sc)
+{
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        double sn, cs;
+        sincos(sc * vec[k], &sn, &cs);
+        cplx a = A[k], b = B[k];
+        if (REAL) {
+            A[k] = c_make(fma(cs, a.x, sn * b.x), fma(cs, a.y, sn * b.y));
+            B[k] = c_make(fma(cs, b.x, -sn * a.x), fma(cs, b.y, -sn * a.y));
+        } else {
+            A[k] = c_make(fma(cs, a.x, sn * b.y), fma(cs, a.y, -sn * b.x));
+            B[k] = c_make(fma(cs, b.x, sn * a.y), fma(cs, b.y, -sn * a.x));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Crank-Nicolson on one channel held in registers:  g <- 2 (1 + i tau H0)^-1 g - g
+//   ( = (1 + i tau H0)^-1 (1 - i tau H0) g ; evolution_methods.py:98-111 + cy.pyx:9-50 )
+// with the LU factors precomputed (k_factor): forward  y_i = g_i + e_{i-1} y_{i-1},
+// backward x_i = w_i y_i + e_i x_{i+1},  e_i = -i (tau off_i) w_i.
+// Each thread runs the two recurrences over its M rows twice: once with a zero inflow to get its chunk's
+// affine map, then -- after a block-wide scan of those maps -- with the true inflow.
+// sm: 4*32 cplx of shared memory private to this call.
+// ---------------------------------------------------------------------------------------------
+template <int M>
+ION_DEVINL void cn_channel(cplx (&g)[M], const cplx *__restrict__ wch, cplx Pt, cplx Qt, const double (&toff)[M],
+                           double toff_prev, int t, int T, cplx *sm)
+{
+    cplx w[M], e[M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        w[k] = ld_c(wch + k * T + t);
+        e[k] = c_make(toff[k] * w[k].y, -toff[k] * w[k].x);
+    }
+    cplx elink = c_zero();
+    if (t > 0) {
+        cplx wp = ld_c(wch + (M - 1) * T + t - 1);
+        elink = c_make(toff_prev * wp.y, -toff_prev * wp.x);
+    }
+    // forward, zero inflow
+    cplx z = g[0];
+#pragma unroll
+    for (int k = 1; k < M; ++k) z = c_fma(e[k - 1], z, g[k]);
+    cplx yin = affine_scan_block_exclusive<true>(Pt, z, sm, sm + 32, t, T);
+    // forward, true inflow; u = w*y
+    cplx u[M];
+    cplx y = c_fma(elink, yin, g[0]);
+    u[0] = c_mul(w[0], y);
+#pragma unroll
+    for (int k = 1; k < M; ++k) {
+        y = c_fma(e[k - 1], y, g[k]);
+        u[k] = c_mul(w[k], y);
+    }
+    // backward, zero inflow
+    z = u[M - 1];
+#pragma unroll
+    for (int k = M - 2; k >= 0; --k) z = c_fma(e[k], z, u[k]);
+    cplx xin = affine_scan_block_exclusive<false>(Qt, z, sm + 64, sm + 96, t, T);
+    // backward, true inflow; out = 2x - g
+    cplx x = c_fma(e[M - 1], xin, u[M - 1]);
+    g[M - 1] = c_make(fma(2.0, x.x, -g[M - 1].x), fma(2.0, x.y, -g[M - 1].y));
+#pragma unroll
+    for (int k = M - 2; k >= 0; --k) {
+        x = c_fma(e[k], x, u[k]);
+        g[k] = c_make(fma(2.0, x.x, -g[k].x), fma(2.0, x.y, -g[k].y));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// r-pair rotations on the rows of ONE thread-distributed vector pair (S rotated by +theta, D by -theta):
+//   S: [[c, s], [-s, c]] on (i, i+1);  D: [[c, -s], [s, c]]       mesh_operators.py:1247-1408, :384-427
+// r_parity 0: pairs (i even, i+1) are thread-local (M even).  r_parity 1: pairs (i odd, i+1); the pair
+// (t*M + M-1, (t+1)*M) straddles two threads: both threads compute their half from values exchanged through
+// shared memory (xs: 4*T cplx).
+// ---------------------------------------------------------------------------------------------
+template <int M, bool WITH_D>
+ION_DEVINL void rpair_layer_even(cplx (&S)[M], cplx (&D)[M], const double (&zv)[M], double sc)
+{
+#pragma unroll
+    for (int k = 0; k < M; k += 2) {
+        double sn, cs;
+        sincos(sc * zv[k], &sn, &cs);
+        cplx s0 = S[k], s1 = S[k + 1];
+        S[k] = c_make(fma(cs, s0.x, sn * s1.x), fma(cs, s0.y, sn * s1.y));
+        S[k + 1] = c_make(fma(cs, s1.x, -sn * s0.x), fma(cs, s1.y, -sn * s0.y));
+        if (WITH_D) {
+            cplx d0 = D[k], d1 = D[k + 1];
+            D[k] = c_make(fma(cs, d0.x, -sn * d1.x), fma(cs, d0.y, -sn * d1.y));
+            D[k + 1] = c_make(fma(cs, d1.x, sn * d0.x), fma(cs, d1.y, sn * d0.y));
+        }
+    }
+}
+
+template <int M, bool WITH_D>
+ION_DEVINL void rpair_layer_odd(cplx (&S)[M], cplx (&D)[M], const double (&zv)[M], double zprev, double sc, int t,
+                                int T, cplx *xs)
+{
+    // publish first and last rows (pre-layer values)
+    xs[t] = S[0];
+    xs[T + t] = S[M - 1];
+    if (WITH_D) {
+        xs[2 * T + t] = D[0];
+        xs[3 * T + t] = D[M - 1];
+    }
+    __syncthreads();
+    cplx nS0 = (t + 1 < T) ? xs[t + 1] : c_zero();         // next thread's first row
+    cplx pSL = (t > 0) ? xs[T + t - 1] : c_zero();         // previous thread's last row
+    cplx nD0 = c_zero(), pDL = c_zero();
+    if (WITH_D) {
+        nD0 = (t + 1 < T) ? xs[2 * T + t + 1] : c_zero();
+        pDL = (t > 0) ? xs[3 * T + t - 1] : c_zero();
+    }
+    __syncthreads();  // xs may be reused by the next layer
+    // interior odd pairs (k, k+1), k = 1, 3, ..., M-3
+#pragma unroll
+    for (int k = 1; k + 1 < M; k += 2) {
+        double sn, cs;
+        sincos(sc * zv[k], &sn, &cs);
+        cplx s0 = S[k], s1 = S[k + 1];
+        S[k] = c_make(fma(cs, s0.x, sn * s1.x), fma(cs, s0.y, sn * s1.y));
+        S[k + 1] = c_make(fma(cs, s1.x, -sn * s0.x), fma(cs, s1.y, -sn * s0.y));
+        if (WITH_D) {
+            cplx d0 = D[k], d1 = D[k + 1];
+            D[k] = c_make(fma(cs, d0.x, -sn * d1.x), fma(cs, d0.y, -sn * d1.y));
+            D[k + 1] = c_make(fma(cs, d1.x, sn * d0.x), fma(cs, d1.y, sn * d0.y));
+        }
+    }
+    {   // my last row is the LOWER member of (t*M+M-1, (t+1)*M); angle zv[M-1] (0 if no such pair)
+        double sn, cs;
+        sincos(sc * zv[M - 1], &sn, &cs);
+        cplx s0 = S[M - 1];
+        S[M - 1] = c_make(fma(cs, s0.x, sn * nS0.x), fma(cs, s0.y, sn * nS0.y));
+        if (WITH_D) {
+            cplx d0 = D[M - 1];
+            D[M - 1] = c_make(fma(cs, d0.x, -sn * nD0.x), fma(cs, d0.y, -sn * nD0.y));
+        }
+    }
+    {   // my first row is the UPPER member of (t*M-1, t*M); angle zprev (0 for t = 0)
+        double sn, cs;
+        sincos(sc * zprev, &sn, &cs);
+        cplx s1 = S[0];
+        S[0] = c_make(fma(cs, s1.x, -sn * pSL.x), fma(cs, s1.y, -sn * pSL.y));
+        if (WITH_D) {
+            cplx d1 = D[0];
+            D[0] = c_make(fma(cs, d1.x, sn * pDL.x), fma(cs, d1.y, sn * pDL.y));
+        }
+    }
+}
+
+template <int M>
+ION_DEVINL void hadamard(cplx (&A)[M], cplx (&B)[M])
+{
+    const double rs2 = 0.70710678118654752440;
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        cplx a = A[k], b = B[k];
+        A[k] = c_make((a.x + b.x) * rs2, (a.y + b.y) * rs2);
+        B[k] = c_make((a.x - b.x) * rs2, (a.y - b.y) * rs2);
+    }
+}
+
+// Hadamard over the l-pair, the two r-sublayers, Hadamard back  (SimilarityOperator, mesh_operators.py:150-204)
+template <int M>
+ION_DEVINL void h2_pair(cplx (&A)[M], cplx (&B)[M], const double (&zv)[M], double zprev, double sc, bool reverse,
+                        int t, int T, cplx *xs)
+{
+    hadamard<M>(A, B);
+    if (!reverse) {
+        rpair_layer_even<M, true>(A, B, zv, sc);
+        rpair_layer_odd<M, true>(A, B, zv, zprev, sc, t, T, xs);
+    } else {
+        rpair_layer_odd<M, true>(A, B, zv, zprev, sc, t, T, xs);
+        rpair_layer_even<M, true>(A, B, zv, sc);
+    }
+    hadamard<M>(A, B);
+}
+
+// =============================================================================================
+// Unit kernels.  grid = (units, batch), block = T.
+// =============================================================================================
+enum : int {
+    PROG_ROT = 0,        // rotation by (s_a + s_b) [+ mask]                       -- LEN even sweep, VEL h1 sweeps
+    PROG_ROT_CN_ROT = 1, // rotation(s_a), CN on both channels, rotation(s_a)      -- LEN odd sweep around CN
+    PROG_H2 = 2,         // Hadamard r-pair bricks                                  -- VEL h2 on even l-pairs
+    PROG_H2_CN_H2 = 3,   // bricks, CN, bricks reversed                             -- VEL h2 on odd l-pairs around CN
+    PROG_CN = 4,         // CN on every channel (unit = channel)                    -- generic path
+    PROG_LINE_SO_LEN = 5,// exp(-i s w_z) * CN * exp(-i s w_z) [+ mask]             -- LineMesh SO length gauge
+    PROG_LINE_SO_VEL = 6,// r-pair rotations even, odd, CN, odd, even [+ mask]      -- LineMesh SO velocity gauge
+};
+
+template <int M, int PROG, int TMAX>
+__global__ void __launch_bounds__(TMAX) k_unit(const UnitParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *sm_scan = reinterpret_cast<cplx *>(smem_raw);  // 2 channels x 128 cplx
+    cplx *xs = sm_scan + 256;                            // 4*T cplx (r-pair exchange)
+
+    const int t = threadIdx.x, T = p.T;
+    const int b = blockIdx.y;
+    int l0;
+    bool pair = true;
+    if (PROG == PROG_CN || PROG == PROG_LINE_SO_LEN || PROG == PROG_LINE_SO_VEL) {
+        l0 = blockIdx.x;
+        pair = false;
+    } else {
+        unit_channels(p, blockIdx.x, l0, pair);
+    }
+    const size_t chan = (size_t)M * T;
+    cplx *base = p.psi + ((size_t)b * p.L + l0) * chan;
+    const double sa = p.scal_a ? p.scal_a[b] : 0.0;
+    const double sb = p.scal_b ? p.scal_b[b] : 0.0;
+
+    cplx A[M], B[M];
+
+    if (PROG == PROG_ROT) {
+        if (!pair && !(p.flags & F_MASK)) return;
+        load_rows<M>(A, base, T, t);
+        if (pair) {
+            load_rows<M>(B, base + chan, T, t);
+            double vec[M];
+            load_vec<M>(vec, p.vec, T, t);
+            double sc = (sa + sb) * p.cl[p.l_begin + l0];
+            if (p.flags & F_REAL_ROT) rotate_pair<M, true>(A, B, vec, sc);
+            else rotate_pair<M, false>(A, B, vec, sc);
+        }
+        if (p.flags & F_MASK) {
+            double mk[M];
+            load_vec<M>(mk, p.mask, T, t);
+#pragma unroll
+            for (int k = 0; k < M; ++k) {
+                A[k] = c_scale(A[k], mk[k]);
+                if (pair) B[k] = c_scale(B[k], mk[k]);
+            }
+        }
+        store_rows<M>(A, base, T, t);
+        if (pair) store_rows<M>(B, base + chan, T, t);
+        return;
+    }
+
+    if (PROG == PROG_H2) {
+        if (!pair) return;
+        load_rows<M>(A, base, T, t);
+        load_rows<M>(B, base + chan, T, t);
+        double zv[M];
+        load_vec<M>(zv, p.zvec, T, t);
+        double sc = sa * p.cl2[p.l_begin + l0];
+        h2_pair<M>(A, B, zv, p.zprev[t], sc, (p.flags & F_H2_REVERSE) != 0, t, T, xs);
+        store_rows<M>(A, base, T, t);
+        store_rows<M>(B, base + chan, T, t);
+        return;
+    }
+
+    // ---- programs containing Crank-Nicolson ----
+    double toff[M];
+    load_vec<M>(toff, p.toff, T, t);
+    const double toff_prev = p.toff_prev[t];
+    load_rows<M>(A, base, T, t);
+    if (pair) load_rows<M>(B, base + chan, T, t);
+
+    if (PROG == PROG_ROT_CN_ROT) {
+        double vec[M];
+        double sc = 0.0;
+        if (pair) {
+            load_vec<M>(vec, p.vec, T, t);
+            sc = sa * p.cl[p.l_begin + l0];
+            rotate_pair<M, false>(A, B, vec, sc);
+        }
+        cn_channel<M>(A, p.w + (size_t)l0 * chan, p.aggP[(size_t)l0 * T + t], p.aggQ[(size_t)l0 * T + t], toff, toff_prev,
+                      t, T, sm_scan);
+        if (pair) {
+            cn_channel<M>(B, p.w + (size_t)(l0 + 1) * chan, p.aggP[(size_t)(l0 + 1) * T + t],
+                          p.aggQ[(size_t)(l0 + 1) * T + t], toff, toff_prev, t, T, sm_scan + 128);
+            rotate_pair<M, false>(A, B, vec, sc);
+        }
+    } else if (PROG == PROG_H2_CN_H2) {
+        double zv[M];
+        double sc = 0.0, zp = 0.0;
+        if (pair) {
+            load_vec<M>(zv, p.zvec, T, t);
+            zp = p.zprev[t];
+            sc = sa * p.cl2[p.l_begin + l0];
+            h2_pair<M>(A, B, zv, zp, sc, false, t, T, xs);  // (oe, oo)
+        }
+        cn_channel<M>(A, p.w + (size_t)l0 * chan, p.aggP[(size_t)l0 * T + t], p.aggQ[(size_t)l0 * T + t], toff, toff_prev,
+                      t, T, sm_scan);
+        if (pair) {
+            cn_channel<M>(B, p.w + (size_t)(l0 + 1) * chan, p.aggP[(size_t)(l0 + 1) * T + t],
+                          p.aggQ[(size_t)(l0 + 1) * T + t], toff, toff_prev, t, T, sm_scan + 128);
+            h2_pair<M>(A, B, zv, zp, sc, true, t, T, xs);  // (oo, oe)
+        }
+    } else if (PROG == PROG_CN) {
+        cn_channel<M>(A, p.w + (size_t)l0 * chan, p.aggP[(size_t)l0 * T + t], p.aggQ[(size_t)l0 * T + t], toff, toff_prev,
+                      t, T, sm_scan);
+        if (p.flags & F_MASK) {
+            double mk[M];
+            load_vec<M>(mk, p.mask, T, t);
+#pragma unroll
+            for (int k = 0; k < M; ++k) A[k] = c_scale(A[k], mk[k]);
+        }
+    } else if (PROG == PROG_LINE_SO_LEN) {
+        // P = exp(-i tau (-q z E)) = exp(-i s w_z)   mesh_operators.py:329-341
+        double vec[M];
+        load_vec<M>(vec, p.vec, T, t);
+        cplx ph[M];
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+            double sn, cs;
+            sincos(sa * vec[k], &sn, &cs);
+            ph[k] = c_make(cs, -sn);
+            A[k] = c_mul(ph[k], A[k]);
+        }
+        cn_channel<M>(A, p.w, p.aggP[t], p.aggQ[t], toff, toff_prev, t, T, sm_scan);
+#pragma unroll
+        for (int k = 0; k < M; ++k) A[k] = c_mul(ph[k], A[k]);
+        if (p.flags & F_MASK) {
+            double mk[M];
+            load_vec<M>(mk, p.mask, T, t);
+#pragma unroll
+            for (int k = 0; k < M; ++k) A[k] = c_scale(A[k], mk[k]);
+        }
+    } else if (PROG == PROG_LINE_SO_VEL) {
+        // theta identical for every z-pair: zvec holds v_pref on rows that start a pair  mesh_operators.py:384-427
+        double zv[M];
+        load_vec<M>(zv, p.zvec, T, t);
+        const double zp = p.zprev[t];
+        rpair_layer_even<M, false>(A, A, zv, sa);
+        rpair_layer_odd<M, false>(A, A, zv, zp, sa, t, T, xs);
+        cn_channel<M>(A, p.w, p.aggP[t], p.aggQ[t], toff, toff_prev, t, T, sm_scan);
+        rpair_layer_odd<M, false>(A, A, zv, zp, sa, t, T, xs);
+        rpair_layer_even<M, false>(A, A, zv, sa);
+        if (p.flags & F_MASK) {
+            double mk[M];
+            load_vec<M>(mk, p.mask, T, t);
+#pragma unroll
+            for (int k = 0; k < M; ++k) A[k] = c_scale(A[k], mk[k]);
+        }
+    }
+    store_rows<M>(A, base, T, t);
+    if (pair) store_rows<M>(B, base + chan, T, t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic l-sweep for an ODD number of channels, where the reference's even/odd membership follows the
+// parity of the flat index j*L + l and therefore alternates with j (mesh_operators.py:1045).
+// One thread per (pair, position); pairs of one sweep are disjoint at fixed j.
+// ---------------------------------------------------------------------------------------------
+struct SweepParams {
+    cplx *psi;
+    const double *vec;
+    const double *cl;
+    const double *mask;
+    const double *scal_a;
+    const double *scal_b;
+    int L, L_total, l_begin, T, M, R;
+    int parity;
+    int flags;
+};
+
+__global__ void k_sweep_flat(const SweepParams p)
+{
+    const int Rp = p.M * p.T;
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= Rp) return;
+    const int l = blockIdx.y;  // local pair index: channels (l, l+1)
+    const int b = blockIdx.z;
+    const int k = pos / p.T, t = pos % p.T;
+    const long long i = (long long)t * p.M + k;
+    if (i >= p.R) return;
+    const int gl = p.l_begin + l;
+    if ((int)((i * (long long)p.L_total + gl) & 1) != p.parity) return;
+    const double s = (p.scal_a ? p.scal_a[b] : 0.0) + (p.scal_b ? p.scal_b[b] : 0.0);
+    cplx *pa = p.psi + ((size_t)b * p.L + l) * Rp + pos;
+    cplx *pb = pa + Rp;
+    cplx a = *pa, bb = *pb;
+    double sn, cs;
+    sincos(s * p.cl[gl] * p.vec[pos], &sn, &cs);
+    if (p.flags & F_REAL_ROT) {
+        *pa = c_make(fma(cs, a.x, sn * bb.x), fma(cs, a.y, sn * bb.y));
+        *pb = c_make(fma(cs, bb.x, -sn * a.x), fma(cs, bb.y, -sn * a.y));
+    } else {
+        *pa = c_make(fma(cs, a.x, sn * bb.y), fma(cs, a.y, -sn * bb.x));
+        *pb = c_make(fma(cs, bb.x, sn * a.y), fma(cs, bb.y, -sn * a.x));
+    }
+}
+
+// point-wise mask over everything (generic path)
+__global__ void k_mask(cplx *psi, const double *mask, int Rp, long long n_channels)
+{
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= Rp) return;
+    const double m = mask[pos];
+    for (long long c = blockIdx.y; c < n_channels; c += gridDim.y) {
+        cplx *q = psi + (size_t)c * Rp + pos;
+        *q = c_scale(*q, m);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LU factors of (1 + i tau H0) per channel, written in the interleaved layout.  One thread per channel
+// (serial Thomas elimination, run once per distinct tau -- the matrices are time-independent for
+// SphericalHarmonicMesh).  h_diag: [L][R] reference layout.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_factor(const cplx *__restrict__ h_diag, const double *__restrict__ h_off, double tau, int L, int R,
+                         int M, int T, cplx *__restrict__ w)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const int Rp = M * T;
+    cplx *wl = w + (size_t)l * Rp;
+    cplx wprev = c_zero();
+    for (int i = 0; i < Rp; ++i) {
+        cplx wi = c_make(1.0, 0.0);
+        if (i < R) {
+            cplx h = h_diag[(size_t)l * R + i];
+            cplx piv = c_make(1.0 - tau * h.y, tau * h.x);  // 1 + i tau h
+            if (i > 0) {
+                double o = tau * h_off[i - 1];               // O = i*o,  O^2 = -o^2
+                piv = c_make(fma(o * o, wprev.x, piv.x), fma(o * o, wprev.y, piv.y));
+            }
+            wi = c_inv(piv);
+            wprev = wi;
+        }
+        wl[(size_t)(i % M) * T + (i / M)] = wi;
+    }
+}
+
+// chunk aggregates P_t = prod_{i=tM-1}^{tM+M-2} e_i, Q_t = prod_{i=tM}^{tM+M-1} e_i, e_i = -i tau off_i w_i
+__global__ void k_aggregates(const cplx *__restrict__ w, const double *__restrict__ toff, int L, int M, int T,
+                             cplx *__restrict__ aggP, cplx *__restrict__ aggQ)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y;
+    if (t >= T) return;
+    const cplx *wl = w + (size_t)l * M * T;
+    cplx P, Q = c_make(1.0, 0.0);
+    if (t == 0) {
+        P = c_zero();
+    } else {
+        cplx wp = wl[(size_t)(M - 1) * T + t - 1];
+        double tp = toff[(size_t)(M - 1) * T + t - 1];
+        P = c_make(tp * wp.y, -tp * wp.x);
+    }
+    for (int k = 0; k < M; ++k) {
+        cplx wk = wl[(size_t)k * T + t];
+        double tk = toff[(size_t)k * T + t];
+        cplx e = c_make(tk * wk.y, -tk * wk.x);
+        if (k < M - 1) P = c_mul(P, e);
+        Q = c_mul(Q, e);
+    }
+    aggP[(size_t)l * T + t] = P;
+    aggQ[(size_t)l * T + t] = Q;
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout conversion  reference [n][R]  <->  interleaved [n][M][T]
+// ---------------------------------------------------------------------------------------------
+__global__ void k_to_internal_c(const cplx *__restrict__ src, cplx *__restrict__ dst, int R, int M, int T, long long n)
+{
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Rp = M * T;
+    if (pos >= Rp) return;
+    const int k = pos / T, t = pos % T;
+    const long long i = (long long)t * M + k;
+    for (long long c = blockIdx.y; c < n; c += gridDim.y)
+        dst[(size_t)c * Rp + pos] = (i < R) ? src[(size_t)c * R + i] : c_zero();
+}
+__global__ void k_from_internal_c(const cplx *__restrict__ src, cplx *__restrict__ dst, int R, int M, int T, long long n)
+{
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Rp = M * T;
+    if (pos >= Rp) return;
+    const int k = pos / T, t = pos % T;
+    const long long i = (long long)t * M + k;
+    if (i >= R) return;
+    for (long long c = blockIdx.y; c < n; c += gridDim.y) dst[(size_t)c * R + i] = src[(size_t)c * Rp + pos];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Observables (kernel 4).  Stage 1: one CTA per (channel, sim) reduces its row(s) to a few partial sums;
+// stage 2 adds the per-channel partials in a fixed order (deterministic, no atomics).
+// partial layout per (b, l): [norm_l, r_l, z_l, h0_l, within_0..within_{nr-1}]
+// ---------------------------------------------------------------------------------------------
+#define ION_MAX_RADII 8
+struct ObserveParams {
+    const cplx *psi;          // [batch][L][Rp]
+    const double *rvec;       // [Rp] permuted r_j (0 padding)
+    const cplx *h_diag;       // [L][R] reference layout (or nullptr)
+    const double *h_off;      // [R-1]
+    const double *cl_z;       // [L_total-1] c_l (for <z>), or nullptr
+    const cplx *state_rows;   // [n_states][Rp] permuted
+    const int *state_first;   // [L+1] CSR offsets: states of local channel l are state_order[first[l]..first[l+1])
+    const int *state_order;   // [n_states]
+    double *partial;          // [batch][L][4 + nr]
+    double *ip_out;           // [batch][n_states][2]
+    double radii[ION_MAX_RADII];
+    int n_radii;
+    int n_states;
+    int L, L_total, l_begin, R, M, T;
+    unsigned what;
+    double ipm;
+    int line;                 // LineMesh: <z> = sum z |g|^2 is the "r" observable; no l coupling
+};
+
+__global__ void __launch_bounds__(256) k_observe(const ObserveParams p)
+{
+    __shared__ double sm[32 * (4 + ION_MAX_RADII)];
+    const int l = blockIdx.x, b = blockIdx.y;
+    const int Rp = p.M * p.T;
+    const cplx *row = p.psi + ((size_t)b * p.L + l) * Rp;
+    const bool has_up = (l + 1 < p.L);
+    const bool want_z = (p.what & 16u) && has_up && !p.line && p.cl_z;
+    const bool want_h = (p.what & 32u) && p.h_diag;
+    double acc[4 + ION_MAX_RADII];
+#pragma unroll
+    for (int q = 0; q < 4 + ION_MAX_RADII; ++q) acc[q] = 0.0;
+    for (int pos = threadIdx.x; pos < Rp; pos += blockDim.x) {
+        const int k = pos / p.T, t = pos % p.T;
+        const int i = t * p.M + k;
+        if (i >= p.R) continue;
+        cplx g = row[pos];
+        double n2 = c_abs2(g);
+        acc[0] += n2;
+        double r = p.rvec ? p.rvec[pos] : 0.0;
+        acc[1] += r * n2;
+        if (want_z) {
+            cplx gu = row[Rp + pos];
+            acc[2] += 2.0 * (g.x * gu.x + g.y * gu.y) * r;
+        }
+        if (want_h) {
+            cplx h = p.h_diag[(size_t)l * p.R + i];
+            double v = h.x * n2;
+            if (i + 1 < p.R) {
+                int i1 = i + 1;
+                cplx gn = row[(size_t)(i1 % p.M) * p.T + (i1 / p.M)];
+                v += 2.0 * p.h_off[i] * (g.x * gn.x + g.y * gn.y);
+            }
+            acc[3] += v;
+        }
+        for (int q = 0; q < p.n_radii; ++q)
+            if (r <= p.radii[q]) acc[4 + q] += n2;
+    }
+    if (want_z) acc[2] *= p.cl_z[p.l_begin + l];
+    block_sum<4 + ION_MAX_RADII>(acc, sm, threadIdx.x, blockDim.x);
+    if (threadIdx.x == 0) {
+        double *out = p.partial + ((size_t)b * p.L + l) * (4 + p.n_radii);
+        out[0] = acc[0];
+        out[1] = acc[1];
+        out[2] = acc[2];
+        out[3] = acc[3];
+        for (int q = 0; q < p.n_radii; ++q) out[4 + q] = acc[4 + q];
+    }
+    // inner products with the test states living in this channel (mesh/meshes.py:1117-1129)
+    if ((p.what & 2u) && p.n_states > 0) {
+        for (int si = p.state_first[l]; si < p.state_first[l + 1]; ++si) {
+            const int s = p.state_order[si];
+            const cplx *sr = p.state_rows + (size_t)s * Rp;
+            double ip[2] = {0.0, 0.0};
+            for (int pos = threadIdx.x; pos < Rp; pos += blockDim.x) {
+                cplx a = sr[pos], g = row[pos];  // conj(a) * g ; padding rows are zero in both
+                ip[0] += a.x * g.x + a.y * g.y;
+                ip[1] += a.x * g.y - a.y * g.x;
+            }
+            block_sum<2>(ip, sm, threadIdx.x, blockDim.x);
+            if (threadIdx.x == 0) {
+                p.ip_out[((size_t)b * p.n_states + s) * 2 + 0] = ip[0] * p.ipm;
+                p.ip_out[((size_t)b * p.n_states + s) * 2 + 1] = ip[1] * p.ipm;
+            }
+        }
+    }
+}
+
+// stage 2: record assembly.  One thread per simulation (L is small compared with the stage-1 work).
+__global__ void k_observe_finish(const double *__restrict__ partial, const double *__restrict__ ip, double *__restrict__ out,
+                                 int batch, int L, int n_states, int n_radii, unsigned what, double ipm, long long rec)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const int np = 4 + n_radii;
+    const double *pb = partial + (size_t)b * L * np;
+    double *o = out + (size_t)b * rec;
+    double sums[4 + ION_MAX_RADII];
+    for (int q = 0; q < np; ++q) sums[q] = 0.0;
+    for (int l = 0; l < L; ++l)
+        for (int q = 0; q < np; ++q) sums[q] += pb[(size_t)l * np + q];
+    long long c = 0;
+    if (what & 1u) o[c++] = sums[0] * ipm;
+    if (what & 2u)
+        for (int s = 0; s < 2 * n_states; ++s) o[c++] = ip[(size_t)b * n_states * 2 + s];
+    if (what & 4u)
+        for (int l = 0; l < L; ++l) o[c++] = fabs(pb[(size_t)l * np] * ipm);
+    if (what & 8u) o[c++] = sums[1] * ipm;
+    if (what & 16u) o[c++] = sums[2] * ipm;
+    if (what & 32u) o[c++] = sums[3] * ipm;
+    if (what & 64u)
+        for (int q = 0; q < n_radii; ++q) o[c++] = sums[4 + q] * ipm;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ion_tdma_c128: general (non-symmetric, matrix given per call) Thomas solve, cy.pyx:9-50.
+// One warp-sized CTA per system: the data is staged through shared memory with coalesced accesses and the
+// two recurrences are run by lane 0 exactly as the reference runs them (two divisions per row).
+// This entry point exists for drop-in parity with cy.tdma; the production path uses cn_channel.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_tdma_general(const cplx *__restrict__ sub, const cplx *__restrict__ diag, const cplx *__restrict__ sup,
+                               const cplx *__restrict__ rhs, cplx *__restrict__ x, long long n, cplx *scratch)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const long long sys = blockIdx.x;
+    // c' and d' live in shared memory when they fit, else in a global scratch of 2n per system
+    cplx *cp = scratch ? scratch + sys * 2 * n : reinterpret_cast<cplx *>(smem_raw);  // [n]
+    cplx *dp = cp + n;                                                                 // [n]
+    const cplx *a = sub + sys * (n - 1), *bdi = diag + sys * n, *c = sup + sys * (n - 1), *d = rhs + sys * n;
+    // stage sup and rhs (coalesced); the recurrence overwrites them with c' and d'
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        cp[i] = (i < n - 1) ? c[i] : c_zero();
+        dp[i] = d[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        cplx inv = c_inv(bdi[0]);
+        cp[0] = c_mul(cp[0], inv);
+        dp[0] = c_mul(dp[0], inv);
+        for (long long i = 1; i < n; ++i) {
+            cplx s = a[i - 1];
+            cplx denom = c_sub(bdi[i], c_mul(s, cp[i - 1]));
+            inv = c_inv(denom);
+            cp[i] = c_mul(cp[i], inv);
+            dp[i] = c_mul(c_sub(dp[i], c_mul(s, dp[i - 1])), inv);
+        }
+        for (long long i = n - 2; i >= 0; --i) dp[i] = c_sub(dp[i], c_mul(cp[i], dp[i + 1]));
+    }
+    __syncthreads();
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) x[sys * n + i] = dp[i];
+}
+
+}  // namespace ion
