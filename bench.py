@@ -198,7 +198,8 @@ def main():
     updates_per_step = n_t * L * R  # per GPU (one sim per GPU)
 
     sim = engine.DeviceSimulation.from_problem(problem, batch=1, device=local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a capturable (non-legacy) stream: the engine replays CUDA graphs on it
+    torch.cuda.set_stream(stream)
     sim.set_stream(stream.cuda_stream)
     what = nat.OBS_NORM | nat.OBS_INNER_PRODUCTS
 

@@ -40,6 +40,38 @@ ION_DEVINL cplx shfl_c(cplx v, int src)
     return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Incremental sincos.  A thread needs cos/sin of several nearby angles theta_k = sc * vec[k] (consecutive radial
+// rows: the angle varies smoothly with r).  One full-range sincos is taken at a base angle; the others are
+// obtained by rotating the base by d = theta_k - theta_0 with a Taylor polynomial when |d| < 2^-6 (truncation
+// error < 2e-22 relative, i.e. below double rounding) and by a full sincos otherwise.  Always derived from the
+// base, never chained, so errors do not accumulate.
+// ---------------------------------------------------------------------------------------------
+struct SinCosBase {
+    double theta, c, s;
+};
+ION_DEVINL SinCosBase sincos_base(double theta)
+{
+    SinCosBase b;
+    b.theta = theta;
+    sincos(theta, &b.s, &b.c);
+    return b;
+}
+ION_DEVINL void sincos_near(const SinCosBase &b, double theta, double *sn, double *cs)
+{
+    const double d = theta - b.theta;
+    if (fabs(d) < 0.015625) {
+        const double d2 = d * d;
+        // sin d = d (1 - d2/6 (1 - d2/20 (1 - d2/42)));  1 - cos d = d2/2 (1 - d2/12 (1 - d2/30 (1 - d2/56)))
+        const double sd = d * fma(-d2 * (1.0 / 6.0), fma(-d2 * (1.0 / 20.0), fma(-d2, 1.0 / 42.0, 1.0), 1.0), 1.0);
+        const double q = 0.5 * d2 * fma(-d2 * (1.0 / 12.0), fma(-d2 * (1.0 / 30.0), fma(-d2, 1.0 / 56.0, 1.0), 1.0), 1.0);
+        *cs = b.c - fma(b.c, q, b.s * sd);
+        *sn = b.s - fma(b.s, q, -b.c * sd);
+    } else {
+        sincos(theta, sn, cs);
+    }
+}
+
 // 128-bit global accesses of one complex128
 ION_DEVINL cplx ld_c(const cplx *p) { return *p; }
 ION_DEVINL void st_c(cplx *p, cplx v) { *p = v; }
@@ -67,8 +99,11 @@ ION_DEVINL void affine_scan_warp(cplx &P, cplx &B, int lane)
 }
 
 // smP/smB: 32 entries each, private to this call site (no reuse hazard inside one kernel phase).
+// `short_range`: the caller guarantees (k_scan_bound, checked on the host when the LU factors are built) that the
+// product of the multipliers over any whole warp is below 1e-30 in magnitude, so the inflow of a warp is its
+// neighbour's aggregate plus one correction term; everything dropped is < 1e-60 relative to the largest entry.
 template <bool FWD>
-ION_DEVINL cplx affine_scan_block_exclusive(cplx P, cplx B, cplx *smP, cplx *smB, int tid, int nthreads)
+ION_DEVINL cplx affine_scan_block_exclusive(cplx P, cplx B, cplx *smP, cplx *smB, int tid, int nthreads, bool short_range)
 {
     const int lane = tid & 31, warp = tid >> 5, nw = nthreads >> 5;
     affine_scan_warp<FWD>(P, B, lane);
@@ -79,12 +114,20 @@ ION_DEVINL cplx affine_scan_block_exclusive(cplx P, cplx B, cplx *smP, cplx *smB
             smB[warp] = B;
         }
         __syncthreads();
-        cplx wP = (lane < nw) ? smP[lane] : c_make(1.0, 0.0);
-        cplx wB = (lane < nw) ? smB[lane] : c_zero();
-        affine_scan_warp<FWD>(wP, wB, lane);
-        int src = FWD ? warp - 1 : warp + 1;
-        cplx v = shfl_c(wB, src & 31);
-        win = (src >= 0 && src < nw) ? v : c_zero();
+        if (short_range) {
+            const int src = FWD ? warp - 1 : warp + 1, src2 = FWD ? warp - 2 : warp + 2;
+            if (src >= 0 && src < nw) {
+                win = smB[src];
+                if (src2 >= 0 && src2 < nw) win = c_fma(smP[src], smB[src2], win);
+            }
+        } else {
+            cplx wP = (lane < nw) ? smP[lane] : c_make(1.0, 0.0);
+            cplx wB = (lane < nw) ? smB[lane] : c_zero();
+            affine_scan_warp<FWD>(wP, wB, lane);
+            int src = FWD ? warp - 1 : warp + 1;
+            cplx v = shfl_c(wB, src & 31);
+            win = (src >= 0 && src < nw) ? v : c_zero();
+        }
     }
     // exclusive inside the warp
     cplx Pe = FWD ? shfl_up_c(P, 1) : shfl_down_c(P, 1);

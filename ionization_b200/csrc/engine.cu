@@ -15,7 +15,9 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -100,7 +102,22 @@ struct ion_sim {
     bool have_h = false, have_coupling = false;
     double factored_tau = 0.0;
     bool factored = false;
+    bool short_scan = false;
     int64_t launch_count = 0;
+
+    // CUDA graphs: chunks of up to GRAPH_CHUNK consecutive steps are captured once and replayed; the kernels of a
+    // captured chunk read their per-step scalars from scal_chunk and write observations to obs_chunk, which are
+    // refilled / drained around every replay with device-to-device copies.
+    struct GraphEntry {
+        cudaGraphExec_t exec = nullptr;
+        int64_t launches = 0;
+    };
+    std::map<std::string, GraphEntry> graphs;
+    double *scal_chunk = nullptr, *obs_chunk = nullptr;
+    size_t obs_chunk_cap = 0;
+    bool own_stream = false;
+    bool use_graphs = true;
+    bool capturing = false;
 
     // profiling
     bool profiling = false;
@@ -114,7 +131,18 @@ struct ion_sim {
                         mask, rvec,     cl,     cl2,   cl_z, scal, state_rows, state_first, state_order, partial, ip_out, obs_out};
         for (void *p : ptrs)
             if (p) cudaFree(p);
+        if (scal_chunk) cudaFree(scal_chunk);
+        if (obs_chunk) cudaFree(obs_chunk);
+        for (auto &g : graphs)
+            if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
         for (auto e : ev) cudaEventDestroy(e);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+    void invalidate_graphs()
+    {
+        for (auto &g : graphs)
+            if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+        graphs.clear();
     }
 };
 
@@ -179,13 +207,6 @@ int launch_unit_prog(ion_sim *s, const ion::UnitParams &p, dim3 grid)
 #define ION_LAUNCH(TMAX)                                                                                            \
     do {                                                                                                            \
         auto kern = ion::k_unit<4, PROG, TMAX>;                                                                     \
-        if (smem > 48 * 1024) {                                                                                     \
-            static bool attr_set[64] = {false};                                                                     \
-            if (!attr_set[s->device & 63]) {                                                                        \
-                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));       \
-                attr_set[s->device & 63] = true;                                                                    \
-            }                                                                                                       \
-        }                                                                                                           \
         kern<<<grid, block, smem, s->stream>>>(p);                                                                  \
     } while (0)
     if (s->tmax == 256) ION_LAUNCH(256);
@@ -193,6 +214,26 @@ int launch_unit_prog(ion_sim *s, const ion::UnitParams &p, dim3 grid)
     else ION_LAUNCH(1024);
 #undef ION_LAUNCH
     CUDA_TRY(cudaGetLastError());
+    return ION_OK;
+}
+
+template <int PROG>
+int set_unit_smem_attr()
+{
+    CUDA_TRY(cudaFuncSetAttribute(ion::k_unit<4, PROG, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    return ION_OK;
+}
+// kernels launched with more than 48 KB of dynamic shared memory (T > 704) need the opt-in; done once at creation,
+// never inside a stream capture
+int prepare_kernels(ion_sim *s)
+{
+    if (unit_smem_bytes(s) <= 48 * 1024) return ION_OK;
+    int rc;
+    if ((rc = set_unit_smem_attr<ion::PROG_ROT>()) || (rc = set_unit_smem_attr<ion::PROG_ROT_CN_ROT>()) ||
+        (rc = set_unit_smem_attr<ion::PROG_H2>()) || (rc = set_unit_smem_attr<ion::PROG_H2_CN_H2>()) ||
+        (rc = set_unit_smem_attr<ion::PROG_CN>()) || (rc = set_unit_smem_attr<ion::PROG_LINE_SO_LEN>()) ||
+        (rc = set_unit_smem_attr<ion::PROG_LINE_SO_VEL>()))
+        return rc;
     return ION_OK;
 }
 
@@ -215,6 +256,7 @@ ion::UnitParams base_params(ion_sim *s)
     p.L = s->L;
     p.T = s->T;
     p.l_begin = s->l_begin;
+    p.short_scan = s->short_scan ? 1 : 0;
     return p;
 }
 
@@ -323,6 +365,7 @@ int ensure_factor(ion_sim *s, double tau)
 {
     if (s->factored && std::fabs(tau - s->factored_tau) <= 1e-9 * std::fabs(tau)) return ION_OK;
     if (!s->have_h) return fail(ION_ESTATE, "ion_sim_set_hamiltonian must be called before stepping");
+    s->invalidate_graphs();  // factor buffers are (re)allocated below
     // toff (host-side, tiny)
     std::vector<double> off(s->h_off_host);
     for (auto &v : off) v *= tau;
@@ -335,6 +378,26 @@ int ensure_factor(ion_sim *s, double tau)
     dim3 g2((s->T + 127) / 128, s->L);
     ion::k_aggregates<<<g2, 128, 0, s->stream>>>(s->w, s->toff, s->L, s->M, s->T, s->aggP, s->aggQ);
     CUDA_TRY(cudaGetLastError());
+    {   // is the cross-warp inflow of the scans short-ranged?  (product of multipliers over any warp < 1e-30)
+        const int nw = s->T / 32, n = s->L * nw;
+        double *d_bound = nullptr;
+        if (int rc = dev_alloc(&d_bound, (size_t)n)) return rc;
+        ion::k_scan_bound<<<(n + 127) / 128, 128, 0, s->stream>>>(s->aggP, s->aggQ, s->L, s->T, d_bound);
+        std::vector<double> hb((size_t)n);
+        cudaError_t e = cudaMemcpyAsync(hb.data(), d_bound, hb.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        cudaFree(d_bound);
+        if (e != cudaSuccess) return fail(ION_ECUDA, std::string("k_scan_bound: ") + cudaGetErrorString(e));
+        double mx = -1e300;
+        for (int l = 0; l < s->L; ++l)
+            for (int w = 0; w < nw; ++w) {
+                // warp 0 in the forward direction / the last warp backwards have no inflow; their bound is irrelevant but harmless
+                mx = std::max(mx, hb[(size_t)l * nw + w]);
+            }
+        s->short_scan = (nw > 1) && (mx < std::log(1e-30));
+        if (const char *env = std::getenv("ION_FULL_SCAN"))
+            if (env[0] == '1') s->short_scan = false;
+    }
     s->factored = true;
     s->factored_tau = tau;
     return ION_OK;
@@ -468,6 +531,30 @@ int ensure_observe_buffers(ion_sim *s, size_t n_records, uint32_t what)
     return ION_OK;
 }
 
+constexpr int64_t GRAPH_CHUNK = 64;
+
+// enqueue steps [n0, n0+len) reading scalars from `scal` (row n - n0 of it) and writing observations to `obs`
+int enqueue_steps(ion_sim *s, int64_t len, const double *scal, const uint8_t *pattern, bool pre_done_first, bool fuse_last,
+                  uint32_t what, double *obs, size_t rec, bool *pre_done_out)
+{
+    const bool can_fuse = program_fuses(s);
+    bool pre_done = pre_done_first;
+    int64_t k_obs = 0;
+    for (int64_t n = 0; n < len; ++n) {
+        const bool ob = pattern && pattern[n];
+        const bool fuse_next = can_fuse && !ob && (n + 1 < len ? true : fuse_last);
+        const double *sa = scal + (size_t)n * s->batch;
+        if (int rc = enqueue_step(s, sa, sa + s->batch, pre_done, fuse_next)) return rc;
+        pre_done = fuse_next;
+        if (ob) {
+            if (int rc = launch_observe(s, what, obs + (size_t)k_obs * rec)) return rc;
+            ++k_obs;
+        }
+    }
+    if (pre_done_out) *pre_done_out = pre_done;
+    return ION_OK;
+}
+
 int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fields, const uint8_t *observe_mask, uint32_t what,
              double *out)
 {
@@ -485,18 +572,94 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
     if (int rc = upload_scalars(s, n_steps, taus, fields)) return rc;
     const size_t rec = (size_t)ion_sim_observation_size(s, what) * s->batch;
     const bool can_fuse = program_fuses(s);
-    bool pre_done = false;
-    int64_t k_obs = 0;
-    for (int64_t n = 0; n < n_steps; ++n) {
-        if (int rc = ensure_factor(s, taus[n])) return rc;
-        const bool obs = observe_mask && observe_mask[n];
-        const bool fuse_next = can_fuse && (n + 1 < n_steps) && !obs;
-        const double *sa = s->scal + (size_t)n * s->batch;
-        if (int rc = enqueue_step(s, sa, sa + s->batch, pre_done, fuse_next)) return rc;
-        pre_done = fuse_next;
-        if (obs) {
-            if (int rc = launch_observe(s, what, s->obs_out + (size_t)k_obs * rec)) return rc;
-            ++k_obs;
+
+    // tau must be constant (to 1e-9 relative: linspace jitter) for the cached LU factors; a changing
+    // time step re-factors between steps and is run with plain launches.
+    bool uniform_tau = true;
+    for (int64_t n = 1; n < n_steps; ++n)
+        if (std::fabs(taus[n] - taus[0]) > 1e-9 * std::fabs(taus[0])) uniform_tau = false;
+
+    if (!(s->use_graphs && uniform_tau && !s->profiling && s->stream != 0 && n_steps >= 4)) {
+        bool pre_done = false;
+        int64_t k_obs = 0;
+        for (int64_t n = 0; n < n_steps; ++n) {
+            if (int rc = ensure_factor(s, taus[n])) return rc;
+            const bool obs = observe_mask && observe_mask[n];
+            const bool fuse_next = can_fuse && (n + 1 < n_steps) && !obs;
+            const double *sa = s->scal + (size_t)n * s->batch;
+            if (int rc = enqueue_step(s, sa, sa + s->batch, pre_done, fuse_next)) return rc;
+            pre_done = fuse_next;
+            if (obs) {
+                if (int rc = launch_observe(s, what, s->obs_out + (size_t)k_obs * rec)) return rc;
+                ++k_obs;
+            }
+        }
+    } else {
+        if (int rc = ensure_factor(s, taus[0])) return rc;
+        if (!s->scal_chunk)
+            if (int rc = dev_alloc(&s->scal_chunk, (size_t)(GRAPH_CHUNK + 1) * s->batch)) return rc;
+        if (n_obs && s->obs_chunk_cap < (size_t)GRAPH_CHUNK * rec) {
+            s->invalidate_graphs();
+            if (int rc = dev_alloc(&s->obs_chunk, (size_t)GRAPH_CHUNK * rec)) return rc;
+            s->obs_chunk_cap = (size_t)GRAPH_CHUNK * rec;
+        }
+        bool pre_done = false;
+        int64_t k_obs = 0;
+        for (int64_t n0 = 0; n0 < n_steps; n0 += GRAPH_CHUNK) {
+            const int64_t len = std::min<int64_t>(GRAPH_CHUNK, n_steps - n0);
+            const uint8_t *pattern = observe_mask ? observe_mask + n0 : nullptr;
+            int64_t obs_here = 0;
+            std::string key(1, (char)(pre_done ? 1 : 0));
+            const bool fuse_last = can_fuse && (n0 + len < n_steps) && !(pattern && pattern[len - 1]);
+            key.push_back((char)(fuse_last ? 1 : 0));
+            key.append(reinterpret_cast<const char *>(&len), sizeof(len));
+            key.append(reinterpret_cast<const char *>(&what), sizeof(what));
+            for (int64_t n = 0; n < len; ++n) {
+                const char ob = (pattern && pattern[n]) ? 1 : 0;
+                obs_here += ob;
+                key.push_back(ob);
+            }
+            auto it = s->graphs.find(key);
+            bool pre_done_after = pre_done;
+            if (it == s->graphs.end()) {
+                ion_sim::GraphEntry entry;
+                cudaGraph_t graph = nullptr;
+                const int64_t before = s->launch_count;
+                CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+                s->capturing = true;
+                int rc = enqueue_steps(s, len, s->scal_chunk, pattern, pre_done, fuse_last, what, s->obs_chunk, rec, &pre_done_after);
+                s->capturing = false;
+                cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+                entry.launches = s->launch_count - before;
+                s->launch_count = before;
+                if (rc) {
+                    if (graph) cudaGraphDestroy(graph);
+                    return rc;
+                }
+                if (e != cudaSuccess) return fail(ION_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+                e = cudaGraphInstantiate(&entry.exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (e != cudaSuccess) return fail(ION_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+                it = s->graphs.emplace(key, entry).first;
+            } else {
+                // same bookkeeping as the capture run
+                bool pd = pre_done;
+                for (int64_t n = 0; n < len; ++n) {
+                    const bool ob = pattern && pattern[n];
+                    pd = can_fuse && !ob && (n + 1 < len ? true : fuse_last);
+                }
+                pre_done_after = pd;
+            }
+            CUDA_TRY(cudaMemcpyAsync(s->scal_chunk, s->scal + (size_t)n0 * s->batch, (size_t)(len + 1) * s->batch * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, s->stream));
+            CUDA_TRY(cudaGraphLaunch(it->second.exec, s->stream));
+            s->launch_count += it->second.launches;
+            if (obs_here) {
+                CUDA_TRY(cudaMemcpyAsync(s->obs_out + (size_t)k_obs * rec, s->obs_chunk, (size_t)obs_here * rec * sizeof(double),
+                                         cudaMemcpyDeviceToDevice, s->stream));
+                k_obs += obs_here;
+            }
+            pre_done = pre_done_after;
         }
     }
     if (n_obs) {
@@ -607,7 +770,11 @@ int ion_sim_create_sharded(int program, int64_t L_total, int64_t l_begin, int64_
     s->Rp = (int)(M * T);
     s->tmax = T <= 256 ? 256 : (T <= 512 ? 512 : 1024);
     s->line = line;
-    int rc = dev_alloc(&s->psi, (size_t)batch * L * s->Rp);
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess) s->own_stream = true;
+    else s->stream = 0;
+    if (const char *env = std::getenv("ION_NO_GRAPHS")) s->use_graphs = !(env[0] == '1');
+    int rc = prepare_kernels(s);
+    if (rc == ION_OK) rc = dev_alloc(&s->psi, (size_t)batch * L * s->Rp);
     if (rc == ION_OK) {
         cudaError_t e = cudaMemset(s->psi, 0, (size_t)batch * L * s->Rp * sizeof(cplx));
         if (e != cudaSuccess) rc = fail(ION_ECUDA, cudaGetErrorString(e));
@@ -637,6 +804,11 @@ int ion_sim_destroy(ion_sim_t *s)
 int ion_sim_set_stream(ion_sim_t *s, void *cuda_stream)
 {
     if (!s) return fail(ION_EINVAL, "sim is NULL");
+    s->invalidate_graphs();
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    s->own_stream = false;
     s->stream = (cudaStream_t)cuda_stream;
     return ION_OK;
 }
@@ -644,6 +816,7 @@ int ion_sim_set_stream(ion_sim_t *s, void *cuda_stream)
 int ion_sim_set_hamiltonian(ion_sim_t *s, const void *h_diag, const double *h_off)
 {
     if (!s || !h_diag || !h_off) return fail(ION_EINVAL, "NULL argument");
+    s->invalidate_graphs();
     CUDA_TRY(cudaSetDevice(s->device));
     if (int rc = dev_alloc(&s->h_diag, (size_t)s->L * s->R)) return rc;
     if (int rc = dev_alloc(&s->h_off, (size_t)s->R - 1)) return rc;
@@ -659,6 +832,7 @@ int ion_sim_set_hamiltonian(ion_sim_t *s, const void *h_diag, const double *h_of
 int ion_sim_set_len_coupling(ion_sim_t *s, const double *c_l, const double *x_j)
 {
     if (!s || !x_j || (s->L_total > 1 && !c_l)) return fail(ION_EINVAL, "NULL argument");
+    s->invalidate_graphs();
     if (s->program != ION_SH_LEN_SO) return fail(ION_EINVAL, "length-gauge coupling does not belong to this program");
     CUDA_TRY(cudaSetDevice(s->device));
     if (int rc = upload_plain(s, c_l, (size_t)s->L_total - 1, &s->cl)) return rc;
@@ -671,6 +845,7 @@ int ion_sim_set_len_coupling(ion_sim_t *s, const double *c_l, const double *x_j)
 int ion_sim_set_vel_coupling(ion_sim_t *s, const double *c_l, const double *f1_l, const double *y_j, const double *z_j)
 {
     if (!s || !y_j || !z_j || (s->L_total > 1 && (!c_l || !f1_l))) return fail(ION_EINVAL, "NULL argument");
+    s->invalidate_graphs();
     if (s->program != ION_SH_VEL_SO) return fail(ION_EINVAL, "velocity-gauge coupling does not belong to this program");
     CUDA_TRY(cudaSetDevice(s->device));
     if (int rc = upload_plain(s, f1_l, (size_t)s->L_total - 1, &s->cl)) return rc;
@@ -685,6 +860,7 @@ int ion_sim_set_vel_coupling(ion_sim_t *s, const double *c_l, const double *f1_l
 int ion_sim_set_line_coupling(ion_sim_t *s, const double *w_z, double v_pref)
 {
     if (!s) return fail(ION_EINVAL, "sim is NULL");
+    s->invalidate_graphs();
     if (!s->line) return fail(ION_EINVAL, "line coupling does not belong to this program");
     CUDA_TRY(cudaSetDevice(s->device));
     if (s->program == ION_LINE_VEL_SO) {
@@ -701,6 +877,7 @@ int ion_sim_set_line_coupling(ion_sim_t *s, const double *w_z, double v_pref)
 int ion_sim_set_mask(ion_sim_t *s, const double *mask)
 {
     if (!s) return fail(ION_EINVAL, "sim is NULL");
+    s->invalidate_graphs();
     CUDA_TRY(cudaSetDevice(s->device));
     if (!mask) {
         if (s->mask) cudaFree(s->mask);
@@ -714,6 +891,7 @@ int ion_sim_set_observables(ion_sim_t *s, double ipm, const double *r_j, int64_t
                             const void *state_rows, int64_t n_radii, const double *radii)
 {
     if (!s) return fail(ION_EINVAL, "sim is NULL");
+    s->invalidate_graphs();
     if (n_radii > ION_MAX_RADII) return fail(ION_ENOTSUP, "at most 8 radii");
     if (n_states < 0 || n_radii < 0 || (n_states > 0 && (!state_l || !state_rows)) || (n_radii > 0 && !radii))
         return fail(ION_EINVAL, "inconsistent observables arguments");

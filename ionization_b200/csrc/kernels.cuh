@@ -45,6 +45,7 @@ struct UnitParams {
     int l_begin;             // global index of owned channel 0
     int parity;              // parity (in GLOBAL l) of the lower channel of a pair
     int flags;
+    int short_scan;          // cross-warp inflow of the CN scans is short-ranged (see common.cuh)
 };
 
 // unit -> (first local channel, is pair).  Pairs are (l, l+1) with global l % 2 == parity.
@@ -93,13 +94,27 @@ ION_DEVINL void load_vec(double (&v)[M], const double *base, int T, int t)
 //   complex: [[cos a, -i sin a], [-i sin a, cos a]]   mesh_operators.py:1055-1075
 //   real:    [[cos a,  sin a], [-sin a,  cos a]]      mesh_operators.py:1204-1245
 // ---------------------------------------------------------------------------------------------
+template <int M>
+struct RotAngles {
+    double c[M], s[M];
+};
+template <int M>
+ION_DEVINL RotAngles<M> rot_angles(const double (&vec)[M], double sc)
+{
+    RotAngles<M> a;
+    const SinCosBase base = sincos_base(sc * vec[0]);
+    a.c[0] = base.c;
+    a.s[0] = base.s;
+#pragma unroll
+    for (int k = 1; k < M; ++k) sincos_near(base, sc * vec[k], &a.s[k], &a.c[k]);
+    return a;
+}
 template <int M, bool REAL>
-ION_DEVINL void rotate_pair(cplx (&A)[M], cplx (&B)[M], const double (&vec)[M], double sc)
+ION_DEVINL void rotate_pair(cplx (&A)[M], cplx (&B)[M], const RotAngles<M> &ang)
 {
 #pragma unroll
     for (int k = 0; k < M; ++k) {
-        double sn, cs;
-        sincos(sc * vec[k], &sn, &cs);
+        const double sn = ang.s[k], cs = ang.c[k];
         cplx a = A[k], b = B[k];
         if (REAL) {
             A[k] = c_make(fma(cs, a.x, sn * b.x), fma(cs, a.y, sn * b.y));
@@ -120,26 +135,40 @@ ION_DEVINL void rotate_pair(cplx (&A)[M], cplx (&B)[M], const double (&vec)[M], 
 // affine map, then -- after a block-wide scan of those maps -- with the true inflow.
 // sm: 4*32 cplx of shared memory private to this call.
 // ---------------------------------------------------------------------------------------------
+// LU factors of one channel for this thread's rows, loaded up-front so that their latency overlaps whatever
+// precedes the Crank-Nicolson solve in the kernel (rotations, r-pair bricks, the other channel's solve).
 template <int M>
-ION_DEVINL void cn_channel(cplx (&g)[M], const cplx *__restrict__ wch, cplx Pt, cplx Qt, const double (&toff)[M],
-                           double toff_prev, int t, int T, cplx *sm)
+struct CnFactors {
+    cplx w[M];   // 1 / pivot
+    cplx wprev;  // w of row t*M - 1 (thread t-1's last row)
+    cplx P, Q;   // chunk aggregates
+};
+template <int M>
+ION_DEVINL void cn_load(CnFactors<M> &f, const cplx *__restrict__ wch, const cplx *__restrict__ aggP,
+                        const cplx *__restrict__ aggQ, int t, int T)
 {
-    cplx w[M], e[M];
 #pragma unroll
-    for (int k = 0; k < M; ++k) {
-        w[k] = ld_c(wch + k * T + t);
-        e[k] = c_make(toff[k] * w[k].y, -toff[k] * w[k].x);
-    }
-    cplx elink = c_zero();
-    if (t > 0) {
-        cplx wp = ld_c(wch + (M - 1) * T + t - 1);
-        elink = c_make(toff_prev * wp.y, -toff_prev * wp.x);
-    }
+    for (int k = 0; k < M; ++k) f.w[k] = ld_c(wch + k * T + t);
+    f.wprev = (t > 0) ? ld_c(wch + (M - 1) * T + t - 1) : c_zero();
+    f.P = ld_c(aggP + t);
+    f.Q = ld_c(aggQ + t);
+}
+
+template <int M>
+ION_DEVINL void cn_channel(cplx (&g)[M], const CnFactors<M> &f, const double (&toff)[M], double toff_prev, int t, int T,
+                           cplx *sm, bool short_scan)
+{
+    const cplx(&w)[M] = f.w;
+    const cplx Pt = f.P, Qt = f.Q;
+    cplx e[M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) e[k] = c_make(toff[k] * w[k].y, -toff[k] * w[k].x);
+    const cplx elink = c_make(toff_prev * f.wprev.y, -toff_prev * f.wprev.x);
     // forward, zero inflow
     cplx z = g[0];
 #pragma unroll
     for (int k = 1; k < M; ++k) z = c_fma(e[k - 1], z, g[k]);
-    cplx yin = affine_scan_block_exclusive<true>(Pt, z, sm, sm + 32, t, T);
+    cplx yin = affine_scan_block_exclusive<true>(Pt, z, sm, sm + 32, t, T, short_scan);
     // forward, true inflow; u = w*y
     cplx u[M];
     cplx y = c_fma(elink, yin, g[0]);
@@ -153,7 +182,7 @@ ION_DEVINL void cn_channel(cplx (&g)[M], const cplx *__restrict__ wch, cplx Pt, 
     z = u[M - 1];
 #pragma unroll
     for (int k = M - 2; k >= 0; --k) z = c_fma(e[k], z, u[k]);
-    cplx xin = affine_scan_block_exclusive<false>(Qt, z, sm + 64, sm + 96, t, T);
+    cplx xin = affine_scan_block_exclusive<false>(Qt, z, sm + 64, sm + 96, t, T, short_scan);
     // backward, true inflow; out = 2x - g
     cplx x = c_fma(e[M - 1], xin, u[M - 1]);
     g[M - 1] = c_make(fma(2.0, x.x, -g[M - 1].x), fma(2.0, x.y, -g[M - 1].y));
@@ -171,13 +200,34 @@ ION_DEVINL void cn_channel(cplx (&g)[M], const cplx *__restrict__ wch, cplx Pt, 
 // (t*M + M-1, (t+1)*M) straddles two threads: both threads compute their half from values exchanged through
 // shared memory (xs: 4*T cplx).
 // ---------------------------------------------------------------------------------------------
+// cos/sin of the r-pair angles of one thread: pairs starting at even local rows k = 0, 2, .. (index k/2), at odd
+// local rows k = 1, 3, .., M-1 (index (k-1)/2; the last one is the pair shared with thread t+1) and the pair
+// (t*M-1, t*M) shared with thread t-1.  One full sincos, the rest incremental (common.cuh).
+template <int M>
+struct RPairAngles {
+    double ce[M / 2], se[M / 2], co[M / 2], so[M / 2], cp, sp;
+};
+template <int M>
+ION_DEVINL RPairAngles<M> rpair_angles(const double (&zv)[M], double zprev, double sc)
+{
+    RPairAngles<M> a;
+    const SinCosBase base = sincos_base(sc * zv[0]);
+    a.ce[0] = base.c;
+    a.se[0] = base.s;
+#pragma unroll
+    for (int k = 2; k < M; k += 2) sincos_near(base, sc * zv[k], &a.se[k / 2], &a.ce[k / 2]);
+#pragma unroll
+    for (int k = 1; k < M; k += 2) sincos_near(base, sc * zv[k], &a.so[k / 2], &a.co[k / 2]);
+    sincos_near(base, sc * zprev, &a.sp, &a.cp);
+    return a;
+}
+
 template <int M, bool WITH_D>
-ION_DEVINL void rpair_layer_even(cplx (&S)[M], cplx (&D)[M], const double (&zv)[M], double sc)
+ION_DEVINL void rpair_layer_even(cplx (&S)[M], cplx (&D)[M], const RPairAngles<M> &ang)
 {
 #pragma unroll
     for (int k = 0; k < M; k += 2) {
-        double sn, cs;
-        sincos(sc * zv[k], &sn, &cs);
+        const double sn = ang.se[k / 2], cs = ang.ce[k / 2];
         cplx s0 = S[k], s1 = S[k + 1];
         S[k] = c_make(fma(cs, s0.x, sn * s1.x), fma(cs, s0.y, sn * s1.y));
         S[k + 1] = c_make(fma(cs, s1.x, -sn * s0.x), fma(cs, s1.y, -sn * s0.y));
@@ -190,8 +240,7 @@ ION_DEVINL void rpair_layer_even(cplx (&S)[M], cplx (&D)[M], const double (&zv)[
 }
 
 template <int M, bool WITH_D>
-ION_DEVINL void rpair_layer_odd(cplx (&S)[M], cplx (&D)[M], const double (&zv)[M], double zprev, double sc, int t,
-                                int T, cplx *xs)
+ION_DEVINL void rpair_layer_odd(cplx (&S)[M], cplx (&D)[M], const RPairAngles<M> &ang, int t, int T, cplx *xs)
 {
     // publish first and last rows (pre-layer values)
     xs[t] = S[0];
@@ -212,8 +261,7 @@ ION_DEVINL void rpair_layer_odd(cplx (&S)[M], cplx (&D)[M], const double (&zv)[M
     // interior odd pairs (k, k+1), k = 1, 3, ..., M-3
 #pragma unroll
     for (int k = 1; k + 1 < M; k += 2) {
-        double sn, cs;
-        sincos(sc * zv[k], &sn, &cs);
+        const double sn = ang.so[k / 2], cs = ang.co[k / 2];
         cplx s0 = S[k], s1 = S[k + 1];
         S[k] = c_make(fma(cs, s0.x, sn * s1.x), fma(cs, s0.y, sn * s1.y));
         S[k + 1] = c_make(fma(cs, s1.x, -sn * s0.x), fma(cs, s1.y, -sn * s0.y));
@@ -223,9 +271,8 @@ ION_DEVINL void rpair_layer_odd(cplx (&S)[M], cplx (&D)[M], const double (&zv)[M
             D[k + 1] = c_make(fma(cs, d1.x, sn * d0.x), fma(cs, d1.y, sn * d0.y));
         }
     }
-    {   // my last row is the LOWER member of (t*M+M-1, (t+1)*M); angle zv[M-1] (0 if no such pair)
-        double sn, cs;
-        sincos(sc * zv[M - 1], &sn, &cs);
+    {   // my last row is the LOWER member of (t*M+M-1, (t+1)*M); its angle is 0 if there is no such pair
+        const double sn = ang.so[M / 2 - 1], cs = ang.co[M / 2 - 1];
         cplx s0 = S[M - 1];
         S[M - 1] = c_make(fma(cs, s0.x, sn * nS0.x), fma(cs, s0.y, sn * nS0.y));
         if (WITH_D) {
@@ -234,8 +281,7 @@ ION_DEVINL void rpair_layer_odd(cplx (&S)[M], cplx (&D)[M], const double (&zv)[M
         }
     }
     {   // my first row is the UPPER member of (t*M-1, t*M); angle zprev (0 for t = 0)
-        double sn, cs;
-        sincos(sc * zprev, &sn, &cs);
+        const double sn = ang.sp, cs = ang.cp;
         cplx s1 = S[0];
         S[0] = c_make(fma(cs, s1.x, -sn * pSL.x), fma(cs, s1.y, -sn * pSL.y));
         if (WITH_D) {
@@ -259,16 +305,15 @@ ION_DEVINL void hadamard(cplx (&A)[M], cplx (&B)[M])
 
 // Hadamard over the l-pair, the two r-sublayers, Hadamard back  (SimilarityOperator, mesh_operators.py:150-204)
 template <int M>
-ION_DEVINL void h2_pair(cplx (&A)[M], cplx (&B)[M], const double (&zv)[M], double zprev, double sc, bool reverse,
-                        int t, int T, cplx *xs)
+ION_DEVINL void h2_pair(cplx (&A)[M], cplx (&B)[M], const RPairAngles<M> &ang, bool reverse, int t, int T, cplx *xs)
 {
     hadamard<M>(A, B);
     if (!reverse) {
-        rpair_layer_even<M, true>(A, B, zv, sc);
-        rpair_layer_odd<M, true>(A, B, zv, zprev, sc, t, T, xs);
+        rpair_layer_even<M, true>(A, B, ang);
+        rpair_layer_odd<M, true>(A, B, ang, t, T, xs);
     } else {
-        rpair_layer_odd<M, true>(A, B, zv, zprev, sc, t, T, xs);
-        rpair_layer_even<M, true>(A, B, zv, sc);
+        rpair_layer_odd<M, true>(A, B, ang, t, T, xs);
+        rpair_layer_even<M, true>(A, B, ang);
     }
     hadamard<M>(A, B);
 }
@@ -286,8 +331,11 @@ enum : int {
     PROG_LINE_SO_VEL = 6,// r-pair rotations even, odd, CN, odd, even [+ mask]      -- LineMesh SO velocity gauge
 };
 
+// register budget: the programs without a Crank-Nicolson solve are asked to fit two CTAs of TMAX threads per SM
+// (<= 64 registers at TMAX = 512) so that one CTA's loads overlap the other's arithmetic
 template <int M, int PROG, int TMAX>
-__global__ void __launch_bounds__(TMAX) k_unit(const UnitParams p)
+__global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) && TMAX <= 512) ? (1024 / TMAX) : 1)
+    k_unit(const UnitParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *sm_scan = reinterpret_cast<cplx *>(smem_raw);  // 2 channels x 128 cplx
@@ -317,9 +365,9 @@ __global__ void __launch_bounds__(TMAX) k_unit(const UnitParams p)
             load_rows<M>(B, base + chan, T, t);
             double vec[M];
             load_vec<M>(vec, p.vec, T, t);
-            double sc = (sa + sb) * p.cl[p.l_begin + l0];
-            if (p.flags & F_REAL_ROT) rotate_pair<M, true>(A, B, vec, sc);
-            else rotate_pair<M, false>(A, B, vec, sc);
+            const RotAngles<M> ang = rot_angles<M>(vec, (sa + sb) * p.cl[p.l_begin + l0]);
+            if (p.flags & F_REAL_ROT) rotate_pair<M, true>(A, B, ang);
+            else rotate_pair<M, false>(A, B, ang);
         }
         if (p.flags & F_MASK) {
             double mk[M];
@@ -342,7 +390,8 @@ __global__ void __launch_bounds__(TMAX) k_unit(const UnitParams p)
         double zv[M];
         load_vec<M>(zv, p.zvec, T, t);
         double sc = sa * p.cl2[p.l_begin + l0];
-        h2_pair<M>(A, B, zv, p.zprev[t], sc, (p.flags & F_H2_REVERSE) != 0, t, T, xs);
+        const RPairAngles<M> ang = rpair_angles<M>(zv, p.zprev[t], sc);
+        h2_pair<M>(A, B, ang, (p.flags & F_H2_REVERSE) != 0, t, T, xs);
         store_rows<M>(A, base, T, t);
         store_rows<M>(B, base + chan, T, t);
         return;
@@ -354,41 +403,42 @@ __global__ void __launch_bounds__(TMAX) k_unit(const UnitParams p)
     const double toff_prev = p.toff_prev[t];
     load_rows<M>(A, base, T, t);
     if (pair) load_rows<M>(B, base + chan, T, t);
+    CnFactors<M> fA, fB;
+    {
+        const bool single_channel_prog = (PROG == PROG_LINE_SO_LEN || PROG == PROG_LINE_SO_VEL);
+        const size_t lw = single_channel_prog ? 0 : (size_t)l0;
+        cn_load<M>(fA, p.w + lw * chan, p.aggP + lw * T, p.aggQ + lw * T, t, T);
+        if (pair) cn_load<M>(fB, p.w + (lw + 1) * chan, p.aggP + (lw + 1) * T, p.aggQ + (lw + 1) * T, t, T);
+    }
 
     if (PROG == PROG_ROT_CN_ROT) {
-        double vec[M];
-        double sc = 0.0;
+        RotAngles<M> ang;
         if (pair) {
+            double vec[M];
             load_vec<M>(vec, p.vec, T, t);
-            sc = sa * p.cl[p.l_begin + l0];
-            rotate_pair<M, false>(A, B, vec, sc);
+            ang = rot_angles<M>(vec, sa * p.cl[p.l_begin + l0]);  // reused after the CN
+            rotate_pair<M, false>(A, B, ang);
         }
-        cn_channel<M>(A, p.w + (size_t)l0 * chan, p.aggP[(size_t)l0 * T + t], p.aggQ[(size_t)l0 * T + t], toff, toff_prev,
-                      t, T, sm_scan);
+        cn_channel<M>(A, fA, toff, toff_prev, t, T, sm_scan, p.short_scan != 0);
         if (pair) {
-            cn_channel<M>(B, p.w + (size_t)(l0 + 1) * chan, p.aggP[(size_t)(l0 + 1) * T + t],
-                          p.aggQ[(size_t)(l0 + 1) * T + t], toff, toff_prev, t, T, sm_scan + 128);
-            rotate_pair<M, false>(A, B, vec, sc);
+            cn_channel<M>(B, fB, toff, toff_prev, t, T, sm_scan + 128, p.short_scan != 0);
+            rotate_pair<M, false>(A, B, ang);
         }
     } else if (PROG == PROG_H2_CN_H2) {
-        double zv[M];
-        double sc = 0.0, zp = 0.0;
+        RPairAngles<M> ang;
         if (pair) {
+            double zv[M];
             load_vec<M>(zv, p.zvec, T, t);
-            zp = p.zprev[t];
-            sc = sa * p.cl2[p.l_begin + l0];
-            h2_pair<M>(A, B, zv, zp, sc, false, t, T, xs);  // (oe, oo)
+            ang = rpair_angles<M>(zv, p.zprev[t], sa * p.cl2[p.l_begin + l0]);  // reused after the CN
+            h2_pair<M>(A, B, ang, false, t, T, xs);  // (oe, oo)
         }
-        cn_channel<M>(A, p.w + (size_t)l0 * chan, p.aggP[(size_t)l0 * T + t], p.aggQ[(size_t)l0 * T + t], toff, toff_prev,
-                      t, T, sm_scan);
+        cn_channel<M>(A, fA, toff, toff_prev, t, T, sm_scan, p.short_scan != 0);
         if (pair) {
-            cn_channel<M>(B, p.w + (size_t)(l0 + 1) * chan, p.aggP[(size_t)(l0 + 1) * T + t],
-                          p.aggQ[(size_t)(l0 + 1) * T + t], toff, toff_prev, t, T, sm_scan + 128);
-            h2_pair<M>(A, B, zv, zp, sc, true, t, T, xs);  // (oo, oe)
+            cn_channel<M>(B, fB, toff, toff_prev, t, T, sm_scan + 128, p.short_scan != 0);
+            h2_pair<M>(A, B, ang, true, t, T, xs);  // (oo, oe)
         }
     } else if (PROG == PROG_CN) {
-        cn_channel<M>(A, p.w + (size_t)l0 * chan, p.aggP[(size_t)l0 * T + t], p.aggQ[(size_t)l0 * T + t], toff, toff_prev,
-                      t, T, sm_scan);
+        cn_channel<M>(A, fA, toff, toff_prev, t, T, sm_scan, p.short_scan != 0);
         if (p.flags & F_MASK) {
             double mk[M];
             load_vec<M>(mk, p.mask, T, t);
@@ -400,14 +450,16 @@ __global__ void __launch_bounds__(TMAX) k_unit(const UnitParams p)
         double vec[M];
         load_vec<M>(vec, p.vec, T, t);
         cplx ph[M];
+        const SinCosBase pbase = sincos_base(sa * vec[0]);
 #pragma unroll
         for (int k = 0; k < M; ++k) {
             double sn, cs;
-            sincos(sa * vec[k], &sn, &cs);
+            if (k == 0) sn = pbase.s, cs = pbase.c;
+            else sincos_near(pbase, sa * vec[k], &sn, &cs);
             ph[k] = c_make(cs, -sn);
             A[k] = c_mul(ph[k], A[k]);
         }
-        cn_channel<M>(A, p.w, p.aggP[t], p.aggQ[t], toff, toff_prev, t, T, sm_scan);
+        cn_channel<M>(A, fA, toff, toff_prev, t, T, sm_scan, p.short_scan != 0);
 #pragma unroll
         for (int k = 0; k < M; ++k) A[k] = c_mul(ph[k], A[k]);
         if (p.flags & F_MASK) {
@@ -420,12 +472,12 @@ __global__ void __launch_bounds__(TMAX) k_unit(const UnitParams p)
         // theta identical for every z-pair: zvec holds v_pref on rows that start a pair  mesh_operators.py:384-427
         double zv[M];
         load_vec<M>(zv, p.zvec, T, t);
-        const double zp = p.zprev[t];
-        rpair_layer_even<M, false>(A, A, zv, sa);
-        rpair_layer_odd<M, false>(A, A, zv, zp, sa, t, T, xs);
-        cn_channel<M>(A, p.w, p.aggP[t], p.aggQ[t], toff, toff_prev, t, T, sm_scan);
-        rpair_layer_odd<M, false>(A, A, zv, zp, sa, t, T, xs);
-        rpair_layer_even<M, false>(A, A, zv, sa);
+        const RPairAngles<M> ang = rpair_angles<M>(zv, p.zprev[t], sa);
+        rpair_layer_even<M, false>(A, A, ang);
+        rpair_layer_odd<M, false>(A, A, ang, t, T, xs);
+        cn_channel<M>(A, fA, toff, toff_prev, t, T, sm_scan, p.short_scan != 0);
+        rpair_layer_odd<M, false>(A, A, ang, t, T, xs);
+        rpair_layer_even<M, false>(A, A, ang);
         if (p.flags & F_MASK) {
             double mk[M];
             load_vec<M>(mk, p.mask, T, t);
@@ -547,6 +599,22 @@ __global__ void k_aggregates(const cplx *__restrict__ w, const double *__restric
     }
     aggP[(size_t)l * T + t] = P;
     aggQ[(size_t)l * T + t] = Q;
+}
+
+// log-magnitude of the product of the chunk multipliers over each warp (32 consecutive threads): the host takes
+// the maximum to decide whether the cross-warp part of the CN scans is short-ranged (common.cuh).
+__global__ void k_scan_bound(const cplx *__restrict__ aggP, const cplx *__restrict__ aggQ, int L, int T, double *__restrict__ out)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (l, warp)
+    const int nw = T / 32;
+    if (idx >= L * nw) return;
+    const int l = idx / nw, w = idx % nw;
+    double sp = 0.0, sq = 0.0;
+    for (int t = w * 32; t < w * 32 + 32; ++t) {
+        sp += 0.5 * log(fmax(c_abs2(aggP[(size_t)l * T + t]), 1e-300));
+        sq += 0.5 * log(fmax(c_abs2(aggQ[(size_t)l * T + t]), 1e-300));
+    }
+    out[idx] = fmax(sp, sq);
 }
 
 // ---------------------------------------------------------------------------------------------

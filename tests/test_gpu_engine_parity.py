@@ -246,3 +246,23 @@ def test_tdma_batched():
     x = eng.tdma((a, b, c), d)
     x_ref = restate.tdma_batched(a, b, c, d)
     assert np.allclose(x, x_ref, rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["c1_sh_len_so_500x50", "known_sh_vel_so_500x200"])
+def test_short_range_and_full_scans_agree(name, monkeypatch):
+    """the short-ranged cross-warp inflow (taken when the LU multipliers decay below 1e-30 over a warp) must be
+    indistinguishable from the full block-wide scan; plain launches and CUDA-graph replay must agree as well"""
+    eng = _engine()
+    p = load_golden(name)
+    n = 200
+    out = {}
+    for mode, env in (("default", {}), ("full_scan", {"ION_FULL_SCAN": "1"}), ("no_graphs", {"ION_NO_GRAPHS": "1"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with eng.DeviceSimulation.from_problem(p) as sim:
+            sim.step(p["taus"][:n], p["fields"][:n])
+            out[mode] = sim.read_g()[0]
+        for k in env:
+            monkeypatch.delenv(k)
+    assert rel_err(out["default"], out["full_scan"]) < 1e-13
+    assert rel_err(out["default"], out["no_graphs"]) == 0.0
