@@ -228,7 +228,7 @@ class MeshSimulation(_Beet):
         self.spec = spec
         self.status = Status.INITIALIZED
         self.device = getattr(spec, "device", 0)
-        self.latest_checkpoint_time = datetime.datetime.utcnow()
+        self.latest_checkpoint_time = datetime.datetime.now(datetime.timezone.utc)
 
         self.times = self.get_times()
         if spec.electric_potential_dc_correction:
@@ -466,7 +466,7 @@ class MeshSimulation(_Beet):
                 self.time_index = n1
 
             if self.spec.checkpoints:
-                now = datetime.datetime.utcnow()
+                now = datetime.datetime.now(datetime.timezone.utc)
                 if (now - self.latest_checkpoint_time) > self.spec.checkpoint_every:
                     self.do_checkpoint(now, checkpoint_callback)
 
