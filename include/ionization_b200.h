@@ -157,8 +157,13 @@ int ion_sim_synchronize(ion_sim_t *sim);
  *   which: 0 = send-to-lower (my first channel), 1 = send-to-upper (my last channel),
  *          2 = recv-from-lower,                   3 = recv-from-upper. */
 int ion_sim_halo_buffer(ion_sim_t *sim, int which, void **device_ptr, int64_t *n_bytes);
-/* number of phases of one step for this program (exchange needed between consecutive phases) */
+/* number of phases (pair-local kernels) of one step of this program, and whether the neighbours' boundary channels
+ * must be delivered into this shard's recv buffers before a given phase.  Shards are cut at even channels, so only
+ * the odd-parity sweeps cross a cut: 1 exchange per step in the length gauge, 3 in the velocity gauge.
+ * A shard holds one ghost channel per neighbour: ion_sim_set_hamiltonian() of a shard takes h_diag for the channels
+ * [l_begin - (l_begin > 0), l_begin + L + (l_begin + L < L_total)), ghosts included. */
 int ion_sim_num_phases(ion_sim_t *sim);
+int ion_sim_phase_needs_halo(ion_sim_t *sim, int phase);
 /* run phase `phase` of the step with scalars tau, field[batch] (host pointers).  Before phase p>0 the caller
  * must have delivered the neighbours' send buffers (filled by phase p-1) into this shard's recv buffers. */
 int ion_sim_step_phase(ion_sim_t *sim, int phase, double tau, const double *field);

@@ -66,6 +66,7 @@ SIGNATURES = {
     "ion_sim_synchronize": (_i32, [_vp]),
     "ion_sim_halo_buffer": (_i32, [_vp, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_i64)]),
     "ion_sim_num_phases": (_i32, [_vp]),
+    "ion_sim_phase_needs_halo": (_i32, [_vp, _i32]),
     "ion_sim_step_phase": (_i32, [_vp, _i32, _f64, _vp]),
     "ion_sim_device_psi": (_i32, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_i64)]),
     "ion_sim_launch_count": (_i64, [_vp]),

@@ -75,8 +75,14 @@ int dev_alloc(T **p, size_t n)
 
 struct ion_sim {
     int program = 0;
+    // L / l_begin describe the channels HELD in psi: the owned ones plus one ghost channel on either side of an
+    // l-block shard (g_lo, g_hi); L_own / l_own are the owned range.  Unsharded: L == L_own == L_total.
     int L = 0, R = 0, batch = 0, device = 0, L_total = 0, l_begin = 0;
-    int M = 4, T = 0, Rp = 0, tmax = 0;
+    int L_own = 0, l_own = 0, g_lo = 0, g_hi = 0;
+    // T = threads per channel (row stride of the layout); a channel is cut into S r-segments of T_seg interior threads,
+    // each CTA running Tc = T_seg + 2H threads (S == 1: Tc == T_seg == T, H == 0)
+    int M = 4, T = 0, Rp = 0, tmax = 0, S = 1, T_seg = 0, H = 0, Tc = 0;
+    double *scal_phase = nullptr;
     bool line = false;
     cudaStream_t stream = 0;
 
@@ -132,6 +138,7 @@ struct ion_sim {
         for (void *p : ptrs)
             if (p) cudaFree(p);
         if (scal_chunk) cudaFree(scal_chunk);
+        if (scal_phase) cudaFree(scal_phase);
         if (obs_chunk) cudaFree(obs_chunk);
         for (auto &g : graphs)
             if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
@@ -197,13 +204,13 @@ void prof_end(ion_sim *s)
     s->ev_kind.push_back(-1);
 }
 
-size_t unit_smem_bytes(const ion_sim *s) { return (256 + 4 * (size_t)s->T) * sizeof(cplx); }
+size_t unit_smem_bytes(const ion_sim *s) { return (256 + 4 * (size_t)s->Tc) * sizeof(cplx); }
 
 template <int PROG>
 int launch_unit_prog(ion_sim *s, const ion::UnitParams &p, dim3 grid)
 {
     const size_t smem = unit_smem_bytes(s);
-    const dim3 block(s->T);
+    const dim3 block(PROG == ion::PROG_ROT ? s->T_seg : s->Tc);
 #define ION_LAUNCH(TMAX)                                                                                            \
     do {                                                                                                            \
         auto kern = ion::k_unit<4, PROG, TMAX>;                                                                     \
@@ -255,6 +262,9 @@ ion::UnitParams base_params(ion_sim *s)
     p.cl2 = s->cl2;
     p.L = s->L;
     p.T = s->T;
+    p.S = s->S;
+    p.T_seg = s->T_seg;
+    p.H = s->H;
     p.l_begin = s->l_begin;
     p.short_scan = s->short_scan ? 1 : 0;
     return p;
@@ -276,7 +286,8 @@ int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, c
         case ion::PROG_LINE_SO_VEL: units = s->L; break;
         default: units = ion::num_units(s->L, s->l_begin, parity);
     }
-    dim3 grid(units, s->batch);
+    dim3 grid(units * s->S, s->batch);
+    if (prog == ion::PROG_ROT) p.H = 0;  // point-wise in r: interior threads only
     int rc = ION_OK;
     switch (prog) {
         case ion::PROG_ROT:
@@ -395,6 +406,10 @@ int ensure_factor(ion_sim *s, double tau)
                 mx = std::max(mx, hb[(size_t)l * nw + w]);
             }
         s->short_scan = (nw > 1) && (mx < std::log(1e-30));
+        if (s->S > 1 && !s->short_scan)
+            return fail(ION_ENOTSUP,
+                        "r_points > 4096 needs the Crank-Nicolson LU multipliers to decay below 1e-30 over 128 rows; this time "
+                        "step is too large for the radial spacing (reduce time_step or increase delta_r)");
         if (const char *env = std::getenv("ION_FULL_SCAN"))
             if (env[0] == '1') s->short_scan = false;
     }
@@ -481,9 +496,10 @@ int launch_observe(ion_sim *s, uint32_t what, double *dev_out)
 {
     ion::ObserveParams p;
     std::memset(&p, 0, sizeof(p));
-    p.psi = s->psi;
+    p.psi = s->psi + (size_t)s->g_lo * s->Rp;
     p.rvec = s->rvec;
-    p.h_diag = s->h_diag;
+    p.h_diag = s->h_diag ? s->h_diag + (size_t)s->g_lo * s->R : nullptr;
+    p.ghost_hi = s->g_hi;
     p.h_off = s->h_off;
     p.cl_z = s->cl_z;
     p.state_rows = s->state_rows;
@@ -494,9 +510,9 @@ int launch_observe(ion_sim *s, uint32_t what, double *dev_out)
     for (int q = 0; q < s->n_radii; ++q) p.radii[q] = s->radii[q];
     p.n_radii = (what & ION_OBS_NORM_WITHIN) ? s->n_radii : 0;
     p.n_states = (what & ION_OBS_INNER_PRODUCTS) ? s->n_states : 0;
-    p.L = s->L;
+    p.L = s->L_own;
     p.L_total = s->L_total;
-    p.l_begin = s->l_begin;
+    p.l_begin = s->l_own;
     p.R = s->R;
     p.M = s->M;
     p.T = s->T;
@@ -504,10 +520,10 @@ int launch_observe(ion_sim *s, uint32_t what, double *dev_out)
     p.ipm = s->ipm;
     p.line = s->line ? 1 : 0;
     prof_begin(s, KK_OBSERVE);
-    ion::k_observe<<<dim3(s->L, s->batch), 256, 0, s->stream>>>(p);
+    ion::k_observe<<<dim3(s->L_own, s->batch), 256, 0, s->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
     long long rec = ion_sim_observation_size(s, what);
-    ion::k_observe_finish<<<(s->batch + 63) / 64, 64, 0, s->stream>>>(s->partial, s->ip_out, dev_out, s->batch, s->L, p.n_states,
+    ion::k_observe_finish<<<(s->batch + 63) / 64, 64, 0, s->stream>>>(s->partial, s->ip_out, dev_out, s->batch, s->L_own, p.n_states,
                                                                      p.n_radii, what, s->ipm, rec);
     prof_end(s);
     s->launch_count += 2;
@@ -518,10 +534,12 @@ int launch_observe(ion_sim *s, uint32_t what, double *dev_out)
 int ensure_observe_buffers(ion_sim *s, size_t n_records, uint32_t what)
 {
     if (!s->partial) {
-        if (int rc = dev_alloc(&s->partial, (size_t)s->batch * s->L * (4 + ION_MAX_RADII))) return rc;
+        if (int rc = dev_alloc(&s->partial, (size_t)s->batch * s->L_own * (4 + ION_MAX_RADII))) return rc;
     }
     if (!s->ip_out) {
-        if (int rc = dev_alloc(&s->ip_out, (size_t)s->batch * std::max(s->n_states, 1) * 2)) return rc;
+        const size_t n = (size_t)s->batch * std::max(s->n_states, 1) * 2;
+        if (int rc = dev_alloc(&s->ip_out, n)) return rc;
+        CUDA_TRY(cudaMemset(s->ip_out, 0, n * sizeof(double)));  // states living in another l-block shard stay 0 here
     }
     size_t need = n_records * s->batch * (size_t)ion_sim_observation_size(s, what);
     if (need > s->obs_cap) {
@@ -563,6 +581,8 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
     if (!taus || !fields) return fail(ION_EINVAL, "taus/fields must not be NULL");
     CUDA_TRY(cudaSetDevice(s->device));
     if (int rc = check_ready(s)) return rc;
+    if (s->L_own != s->L_total)
+        return fail(ION_ESTATE, "an l-block shard is advanced with ion_sim_step_phase (halo exchange between phases)");
     int64_t n_obs = 0;
     if (observe_mask)
         for (int64_t n = 0; n < n_steps; ++n) n_obs += observe_mask[n] ? 1 : 0;
@@ -749,26 +769,48 @@ int ion_sim_create_sharded(int program, int64_t L_total, int64_t l_begin, int64_
     if (line && L_total != 1) return fail(ION_EINVAL, "LineMesh programs need L = 1");
     if (program == ION_SH_LEN_ADI) return fail(ION_ENOTSUP, "ION_SH_LEN_ADI is not implemented in this build");
     if (program == ION_LINE_LEN_CN) return fail(ION_ENOTSUP, "ION_LINE_LEN_CN is not implemented in this build");
-    if (L != L_total) return fail(ION_ENOTSUP, "l-block sharding is not implemented in this build");
+    const bool sharded = (L != L_total);
+    if (sharded) {
+        if (batch != 1) return fail(ION_ENOTSUP, "l-block shards hold one simulation (batch = 1)");
+        if (program != ION_SH_LEN_SO && program != ION_SH_VEL_SO) return fail(ION_ENOTSUP, "l-block sharding: split-operator SphericalHarmonic programs only");
+        if ((L_total % 2) != 0) return fail(ION_ENOTSUP, "l-block sharding needs an even l_bound");
+        if ((l_begin % 2) != 0 || (((l_begin + L) % 2) != 0 && l_begin + L != L_total))
+            return fail(ION_EINVAL, "l-block shards must begin and end on even channels (so that only odd sweeps cross a cut)");
+    }
     if (ion_device_count() <= device || device < 0)
         return fail(ION_ENODEVICE, "no CUDA device " + std::to_string(device) + " (the engine has no CPU path)");
     const int M = 4;
     int64_t T = (R + M - 1) / M;
     T = (T + 31) / 32 * 32;
-    if (T > 1024) return fail(ION_ENOTSUP, "r_points > 4096 is not supported by this build");
+    int S = 1, T_seg = (int)T, H = 0;
+    if (T > 1024) {  // r-segments with halos (kernels.cuh)
+        T_seg = 384;
+        H = 64;
+        S = (int)((T + T_seg - 1) / T_seg);
+        T = (int64_t)S * T_seg;
+    }
     CUDA_TRY(cudaSetDevice(device));
     ion_sim *s = new ion_sim();
     s->program = program;
-    s->L = (int)L;
+    s->g_lo = (sharded && l_begin > 0) ? 1 : 0;
+    s->g_hi = (sharded && l_begin + L < L_total) ? 1 : 0;
+    s->L_own = (int)L;
+    s->l_own = (int)l_begin;
+    s->L = (int)L + s->g_lo + s->g_hi;
+    s->l_begin = (int)l_begin - s->g_lo;
+    L = s->L;
     s->R = (int)R;
     s->batch = (int)batch;
     s->device = device;
     s->L_total = (int)L_total;
-    s->l_begin = (int)l_begin;
     s->M = M;
     s->T = (int)T;
+    s->S = S;
+    s->T_seg = T_seg;
+    s->H = H;
+    s->Tc = T_seg + 2 * H;
     s->Rp = (int)(M * T);
-    s->tmax = T <= 256 ? 256 : (T <= 512 ? 512 : 1024);
+    s->tmax = s->Tc <= 256 ? 256 : (s->Tc <= 512 ? 512 : 1024);
     s->line = line;
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess) s->own_stream = true;
     else s->stream = 0;
@@ -908,13 +950,13 @@ int ion_sim_set_observables(ion_sim_t *s, double ipm, const double *r_j, int64_t
         cudaFree(s->ip_out);
         s->ip_out = nullptr;
     }
-    std::vector<int> first((size_t)s->L + 1, 0), order;
-    for (int l = 0; l < s->L; ++l) {
+    std::vector<int> first((size_t)s->L_own + 1, 0), order;
+    for (int l = 0; l < s->L_own; ++l) {
         first[l] = (int)order.size();
         for (int64_t k = 0; k < n_states; ++k)
-            if (state_l[k] == s->l_begin + l) order.push_back((int)k);
+            if (state_l[k] == s->l_own + l) order.push_back((int)k);
     }
-    first[s->L] = (int)order.size();
+    first[s->L_own] = (int)order.size();
     for (int64_t k = 0; k < n_states; ++k)
         if (state_l[k] < 0 || state_l[k] >= s->L_total) return fail(ION_EINVAL, "state_l out of range");
     if (int rc = dev_alloc(&s->state_first, first.size())) return rc;
@@ -945,12 +987,12 @@ int ion_sim_write_g(ion_sim_t *s, const void *g)
 {
     if (!s || !g) return fail(ION_EINVAL, "NULL argument");
     CUDA_TRY(cudaSetDevice(s->device));
-    const size_t n = (size_t)s->batch * s->L;
+    const size_t n = (size_t)s->batch * s->L_own;  // sharded: batch == 1, ghosts are not part of g
     if (!s->io_stage)
         if (int rc = dev_alloc(&s->io_stage, n * s->R)) return rc;
     CUDA_TRY(cudaMemcpyAsync(s->io_stage, g, n * s->R * sizeof(cplx), cudaMemcpyHostToDevice, s->stream));
     dim3 grid((s->Rp + 127) / 128, (unsigned)std::min<size_t>(n, 8192));
-    ion::k_to_internal_c<<<grid, 128, 0, s->stream>>>(s->io_stage, s->psi, s->R, s->M, s->T, (long long)n);
+    ion::k_to_internal_c<<<grid, 128, 0, s->stream>>>(s->io_stage, s->psi + (size_t)s->g_lo * s->Rp, s->R, s->M, s->T, (long long)n);
     s->launch_count++;
     CUDA_TRY(cudaGetLastError());
     return ION_OK;
@@ -960,11 +1002,11 @@ int ion_sim_read_g(ion_sim_t *s, void *g)
 {
     if (!s || !g) return fail(ION_EINVAL, "NULL argument");
     CUDA_TRY(cudaSetDevice(s->device));
-    const size_t n = (size_t)s->batch * s->L;
+    const size_t n = (size_t)s->batch * s->L_own;
     if (!s->io_stage)
         if (int rc = dev_alloc(&s->io_stage, n * s->R)) return rc;
     dim3 grid((s->Rp + 127) / 128, (unsigned)std::min<size_t>(n, 8192));
-    ion::k_from_internal_c<<<grid, 128, 0, s->stream>>>(s->psi, s->io_stage, s->R, s->M, s->T, (long long)n);
+    ion::k_from_internal_c<<<grid, 128, 0, s->stream>>>(s->psi + (size_t)s->g_lo * s->Rp, s->io_stage, s->R, s->M, s->T, (long long)n);
     s->launch_count++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(g, s->io_stage, n * s->R * sizeof(cplx), cudaMemcpyDeviceToHost, s->stream));
@@ -984,7 +1026,7 @@ int64_t ion_sim_observation_size(ion_sim_t *s, uint32_t what)
     int64_t n = 0;
     if (what & ION_OBS_NORM) n += 1;
     if (what & ION_OBS_INNER_PRODUCTS) n += 2 * (int64_t)s->n_states;
-    if (what & ION_OBS_NORM_BY_L) n += s->L;
+    if (what & ION_OBS_NORM_BY_L) n += s->L_own;
     if (what & ION_OBS_R) n += 1;
     if (what & ION_OBS_Z) n += 1;
     if (what & ION_OBS_H0) n += 1;
@@ -1022,9 +1064,87 @@ int ion_sim_synchronize(ion_sim_t *s)
     return ION_OK;
 }
 
-int ion_sim_halo_buffer(ion_sim_t *, int, void **, int64_t *) { return fail(ION_ENOTSUP, "l-block sharding is not implemented in this build"); }
-int ion_sim_num_phases(ion_sim_t *) { return 1; }
-int ion_sim_step_phase(ion_sim_t *, int, double, const double *) { return fail(ION_ENOTSUP, "l-block sharding is not implemented in this build"); }
+int ion_sim_halo_buffer(ion_sim_t *s, int which, void **device_ptr, int64_t *n_bytes)
+{
+    if (!s || !device_ptr || !n_bytes) return fail(ION_EINVAL, "NULL argument");
+    if (which < 0 || which > 3) return fail(ION_EINVAL, "which must be 0..3");
+    const size_t chan = (size_t)s->Rp;
+    *n_bytes = (int64_t)(chan * sizeof(cplx));
+    cplx *ptr = nullptr;
+    switch (which) {
+        case 0: ptr = s->psi + (size_t)s->g_lo * chan; break;                                   // send to lower: first owned
+        case 1: ptr = s->psi + (size_t)(s->g_lo + s->L_own - 1) * chan; break;                  // send to upper: last owned
+        case 2: ptr = s->g_lo ? s->psi : nullptr; break;                                        // recv from lower: ghost
+        case 3: ptr = s->g_hi ? s->psi + (size_t)(s->g_lo + s->L_own) * chan : nullptr; break;  // recv from upper: ghost
+    }
+    *device_ptr = ptr;
+    return ION_OK;
+}
+
+namespace {
+struct Phase {
+    int prog, parity, flags;
+};
+// one UNFUSED step as a list of pair-local kernels (same order as enqueue_step)
+int phases_of(const ion_sim *s, Phase *out)
+{
+    using namespace ion;
+    if (s->program == ION_SH_LEN_SO) {
+        out[0] = {PROG_ROT, 0, 0};
+        out[1] = {PROG_ROT_CN_ROT, 1, 0};
+        out[2] = {PROG_ROT, 0, F_MASK};
+        return 3;
+    }
+    if (s->program == ION_SH_VEL_SO) {
+        out[0] = {PROG_ROT, 0, F_REAL_ROT};
+        out[1] = {PROG_ROT, 1, F_REAL_ROT};
+        out[2] = {PROG_H2, 0, 0};
+        out[3] = {PROG_H2_CN_H2, 1, 0};
+        out[4] = {PROG_H2, 0, F_H2_REVERSE};
+        out[5] = {PROG_ROT, 1, F_REAL_ROT};
+        out[6] = {PROG_ROT, 0, F_REAL_ROT | F_MASK};
+        return 7;
+    }
+    return 0;
+}
+}  // namespace
+
+int ion_sim_num_phases(ion_sim_t *s)
+{
+    if (!s) return 0;
+    Phase ph[8];
+    return phases_of(s, ph);
+}
+
+int ion_sim_phase_needs_halo(ion_sim_t *s, int phase)
+{
+    if (!s) return 0;
+    Phase ph[8];
+    const int n = phases_of(s, ph);
+    if (phase < 0 || phase >= n) return 0;
+    return ph[phase].parity == 1 ? 1 : 0;  // shards are cut at even channels: only odd-parity pairs straddle a cut
+}
+
+int ion_sim_step_phase(ion_sim_t *s, int phase, double tau, const double *field)
+{
+    if (!s || !field) return fail(ION_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (int rc = check_ready(s)) return rc;
+    Phase ph[8];
+    const int n = phases_of(s, ph);
+    if (n == 0) return fail(ION_ENOTSUP, "program has no phase decomposition");
+    if (phase < 0 || phase >= n) return fail(ION_EINVAL, "phase out of range");
+    if (int rc = ensure_factor(s, tau)) return rc;
+    if (!s->scal_phase)
+        if (int rc = dev_alloc(&s->scal_phase, (size_t)s->batch)) return rc;
+    if (phase == 0) {
+        std::vector<double> h((size_t)s->batch);
+        for (int b = 0; b < s->batch; ++b) h[b] = tau * field[b];
+        CUDA_TRY(cudaMemcpyAsync(s->scal_phase, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    }
+    return launch_unit(s, ph[phase].prog, ph[phase].parity, ph[phase].flags, s->scal_phase, nullptr);
+}
 
 int ion_sim_device_psi(ion_sim_t *s, void **device_ptr, int64_t *n_bytes)
 {

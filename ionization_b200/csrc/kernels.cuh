@@ -40,9 +40,12 @@ struct UnitParams {
     const double *cl2;       // [L_total-1] l-pair coefficient for the r-pair rotations
     const double *scal_a;    // [batch] per-simulation scalar s = tau*field of this step (or nullptr = 0)
     const double *scal_b;    // [batch] second scalar fused in (next step's), or nullptr
-    int L;                   // owned channels
-    int T;
-    int l_begin;             // global index of owned channel 0
+    int L;                   // channels held in psi (owned + ghost channels of an l-block shard)
+    int T;                   // TT: threads per channel = row stride of the interleaved layout (Rp = M * TT)
+    int S;                   // r-segments per channel (1: the CTA covers the whole channel)
+    int T_seg;               // interior threads of a segment
+    int H;                   // halo threads on each side of a segment (0 when S == 1)
+    int l_begin;             // global index of channel 0 of psi
     int parity;              // parity (in GLOBAL l) of the lower channel of a pair
     int flags;
     int short_scan;          // cross-warp inflow of the CN scans is short-ranged (see common.cuh)
@@ -70,23 +73,25 @@ inline int num_units(int L, int l_begin, int parity)
     return lp == 0 ? (L + 1) / 2 : 1 + L / 2;
 }
 
+// `ok`: the thread maps to an existing row chunk of the channel (halo threads beyond either end of it do not)
 template <int M>
-ION_DEVINL void load_rows(cplx (&g)[M], const cplx *base, int T, int t)
+ION_DEVINL void load_rows(cplx (&g)[M], const cplx *base, int T, int t, bool ok)
 {
 #pragma unroll
-    for (int k = 0; k < M; ++k) g[k] = ld_c(base + k * T + t);
+    for (int k = 0; k < M; ++k) g[k] = ok ? ld_c(base + (size_t)k * T + t) : c_zero();
 }
 template <int M>
-ION_DEVINL void store_rows(const cplx (&g)[M], cplx *base, int T, int t)
+ION_DEVINL void store_rows(const cplx (&g)[M], cplx *base, int T, int t, bool ok)
 {
+    if (!ok) return;
 #pragma unroll
-    for (int k = 0; k < M; ++k) st_c(base + k * T + t, g[k]);
+    for (int k = 0; k < M; ++k) st_c(base + (size_t)k * T + t, g[k]);
 }
 template <int M>
-ION_DEVINL void load_vec(double (&v)[M], const double *base, int T, int t)
+ION_DEVINL void load_vec(double (&v)[M], const double *base, int T, int t, bool ok)
 {
 #pragma unroll
-    for (int k = 0; k < M; ++k) v[k] = base[k * T + t];
+    for (int k = 0; k < M; ++k) v[k] = ok ? base[(size_t)k * T + t] : 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -145,13 +150,13 @@ struct CnFactors {
 };
 template <int M>
 ION_DEVINL void cn_load(CnFactors<M> &f, const cplx *__restrict__ wch, const cplx *__restrict__ aggP,
-                        const cplx *__restrict__ aggQ, int t, int T)
+                        const cplx *__restrict__ aggQ, int t, int T, bool ok)
 {
 #pragma unroll
-    for (int k = 0; k < M; ++k) f.w[k] = ld_c(wch + k * T + t);
-    f.wprev = (t > 0) ? ld_c(wch + (M - 1) * T + t - 1) : c_zero();
-    f.P = ld_c(aggP + t);
-    f.Q = ld_c(aggQ + t);
+    for (int k = 0; k < M; ++k) f.w[k] = ok ? ld_c(wch + (size_t)k * T + t) : c_make(1.0, 0.0);
+    f.wprev = (ok && t > 0) ? ld_c(wch + (size_t)(M - 1) * T + t - 1) : c_zero();
+    f.P = ok ? ld_c(aggP + t) : c_zero();
+    f.Q = ok ? ld_c(aggQ + t) : c_zero();
 }
 
 template <int M>
@@ -333,23 +338,34 @@ enum : int {
 
 // register budget: the programs without a Crank-Nicolson solve are asked to fit two CTAs of TMAX threads per SM
 // (<= 64 registers at TMAX = 512) so that one CTA's loads overlap the other's arithmetic
+//
+// r-SEGMENTS.  A channel longer than one CTA can hold (r_points > 4096) is cut into S segments of T_seg threads.
+// Each CTA also computes H halo threads (H*M rows) on either side: the r-pair bricks need their neighbours, and the
+// Crank-Nicolson recurrences are simply started from zero at the edge of the halo.  That is exact to < 1e-30
+// because the LU multipliers decay geometrically -- the host verifies (k_scan_bound) that their product over any 32
+// threads is below 1e-30 before it allows S > 1.  Halo results are discarded; only interior threads store.
 template <int M, int PROG, int TMAX>
 __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) && TMAX <= 512) ? (1024 / TMAX) : 1)
     k_unit(const UnitParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *sm_scan = reinterpret_cast<cplx *>(smem_raw);  // 2 channels x 128 cplx
-    cplx *xs = sm_scan + 256;                            // 4*T cplx (r-pair exchange)
+    cplx *xs = sm_scan + 256;                            // 4*blockDim cplx (r-pair exchange)
 
-    const int t = threadIdx.x, T = p.T;
+    const int tl = threadIdx.x, Tc = blockDim.x;         // index inside the CTA: scans and exchanges
+    const int T = p.T;                                   // row stride of the layout
+    const int seg = blockIdx.x % p.S, unit = blockIdx.x / p.S;
+    const int t = seg * p.T_seg - p.H + tl;              // thread index inside the channel: addressing
+    const bool ok = (t >= 0) && (t < T);
+    const bool mine = ok && (tl >= p.H) && (tl < p.H + p.T_seg);
     const int b = blockIdx.y;
     int l0;
     bool pair = true;
     if (PROG == PROG_CN || PROG == PROG_LINE_SO_LEN || PROG == PROG_LINE_SO_VEL) {
-        l0 = blockIdx.x;
+        l0 = unit;
         pair = false;
     } else {
-        unit_channels(p, blockIdx.x, l0, pair);
+        unit_channels(p, unit, l0, pair);
     }
     const size_t chan = (size_t)M * T;
     cplx *base = p.psi + ((size_t)b * p.L + l0) * chan;
@@ -360,95 +376,97 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
 
     if (PROG == PROG_ROT) {
         if (!pair && !(p.flags & F_MASK)) return;
-        load_rows<M>(A, base, T, t);
+        if (!mine) return;  // point-wise in r: no halo needed (launched with H = 0)
+        load_rows<M>(A, base, T, t, true);
         if (pair) {
-            load_rows<M>(B, base + chan, T, t);
+            load_rows<M>(B, base + chan, T, t, true);
             double vec[M];
-            load_vec<M>(vec, p.vec, T, t);
+            load_vec<M>(vec, p.vec, T, t, true);
             const RotAngles<M> ang = rot_angles<M>(vec, (sa + sb) * p.cl[p.l_begin + l0]);
             if (p.flags & F_REAL_ROT) rotate_pair<M, true>(A, B, ang);
             else rotate_pair<M, false>(A, B, ang);
         }
         if (p.flags & F_MASK) {
             double mk[M];
-            load_vec<M>(mk, p.mask, T, t);
+            load_vec<M>(mk, p.mask, T, t, true);
 #pragma unroll
             for (int k = 0; k < M; ++k) {
                 A[k] = c_scale(A[k], mk[k]);
                 if (pair) B[k] = c_scale(B[k], mk[k]);
             }
         }
-        store_rows<M>(A, base, T, t);
-        if (pair) store_rows<M>(B, base + chan, T, t);
+        store_rows<M>(A, base, T, t, true);
+        if (pair) store_rows<M>(B, base + chan, T, t, true);
         return;
     }
 
     if (PROG == PROG_H2) {
         if (!pair) return;
-        load_rows<M>(A, base, T, t);
-        load_rows<M>(B, base + chan, T, t);
+        load_rows<M>(A, base, T, t, ok);
+        load_rows<M>(B, base + chan, T, t, ok);
         double zv[M];
-        load_vec<M>(zv, p.zvec, T, t);
+        load_vec<M>(zv, p.zvec, T, t, ok);
         double sc = sa * p.cl2[p.l_begin + l0];
-        const RPairAngles<M> ang = rpair_angles<M>(zv, p.zprev[t], sc);
-        h2_pair<M>(A, B, ang, (p.flags & F_H2_REVERSE) != 0, t, T, xs);
-        store_rows<M>(A, base, T, t);
-        store_rows<M>(B, base + chan, T, t);
+        const RPairAngles<M> ang = rpair_angles<M>(zv, ok ? p.zprev[t] : 0.0, sc);
+        h2_pair<M>(A, B, ang, (p.flags & F_H2_REVERSE) != 0, tl, Tc, xs);
+        store_rows<M>(A, base, T, t, mine);
+        store_rows<M>(B, base + chan, T, t, mine);
         return;
     }
 
     // ---- programs containing Crank-Nicolson ----
     double toff[M];
-    load_vec<M>(toff, p.toff, T, t);
-    const double toff_prev = p.toff_prev[t];
-    load_rows<M>(A, base, T, t);
-    if (pair) load_rows<M>(B, base + chan, T, t);
+    load_vec<M>(toff, p.toff, T, t, ok);
+    const double toff_prev = ok ? p.toff_prev[t] : 0.0;
+    load_rows<M>(A, base, T, t, ok);
+    if (pair) load_rows<M>(B, base + chan, T, t, ok);
     CnFactors<M> fA, fB;
     {
         const bool single_channel_prog = (PROG == PROG_LINE_SO_LEN || PROG == PROG_LINE_SO_VEL);
         const size_t lw = single_channel_prog ? 0 : (size_t)l0;
-        cn_load<M>(fA, p.w + lw * chan, p.aggP + lw * T, p.aggQ + lw * T, t, T);
-        if (pair) cn_load<M>(fB, p.w + (lw + 1) * chan, p.aggP + (lw + 1) * T, p.aggQ + (lw + 1) * T, t, T);
+        cn_load<M>(fA, p.w + lw * chan, p.aggP + lw * T, p.aggQ + lw * T, t, T, ok);
+        if (pair) cn_load<M>(fB, p.w + (lw + 1) * chan, p.aggP + (lw + 1) * T, p.aggQ + (lw + 1) * T, t, T, ok);
     }
+    const bool short_scan = p.short_scan != 0;
 
     if (PROG == PROG_ROT_CN_ROT) {
         RotAngles<M> ang;
         if (pair) {
             double vec[M];
-            load_vec<M>(vec, p.vec, T, t);
+            load_vec<M>(vec, p.vec, T, t, ok);
             ang = rot_angles<M>(vec, sa * p.cl[p.l_begin + l0]);  // reused after the CN
             rotate_pair<M, false>(A, B, ang);
         }
-        cn_channel<M>(A, fA, toff, toff_prev, t, T, sm_scan, p.short_scan != 0);
+        cn_channel<M>(A, fA, toff, toff_prev, tl, Tc, sm_scan, short_scan);
         if (pair) {
-            cn_channel<M>(B, fB, toff, toff_prev, t, T, sm_scan + 128, p.short_scan != 0);
+            cn_channel<M>(B, fB, toff, toff_prev, tl, Tc, sm_scan + 128, short_scan);
             rotate_pair<M, false>(A, B, ang);
         }
     } else if (PROG == PROG_H2_CN_H2) {
         RPairAngles<M> ang;
         if (pair) {
             double zv[M];
-            load_vec<M>(zv, p.zvec, T, t);
-            ang = rpair_angles<M>(zv, p.zprev[t], sa * p.cl2[p.l_begin + l0]);  // reused after the CN
-            h2_pair<M>(A, B, ang, false, t, T, xs);  // (oe, oo)
+            load_vec<M>(zv, p.zvec, T, t, ok);
+            ang = rpair_angles<M>(zv, ok ? p.zprev[t] : 0.0, sa * p.cl2[p.l_begin + l0]);  // reused after the CN
+            h2_pair<M>(A, B, ang, false, tl, Tc, xs);  // (oe, oo)
         }
-        cn_channel<M>(A, fA, toff, toff_prev, t, T, sm_scan, p.short_scan != 0);
+        cn_channel<M>(A, fA, toff, toff_prev, tl, Tc, sm_scan, short_scan);
         if (pair) {
-            cn_channel<M>(B, fB, toff, toff_prev, t, T, sm_scan + 128, p.short_scan != 0);
-            h2_pair<M>(A, B, ang, true, t, T, xs);  // (oo, oe)
+            cn_channel<M>(B, fB, toff, toff_prev, tl, Tc, sm_scan + 128, short_scan);
+            h2_pair<M>(A, B, ang, true, tl, Tc, xs);  // (oo, oe)
         }
     } else if (PROG == PROG_CN) {
-        cn_channel<M>(A, fA, toff, toff_prev, t, T, sm_scan, p.short_scan != 0);
+        cn_channel<M>(A, fA, toff, toff_prev, tl, Tc, sm_scan, short_scan);
         if (p.flags & F_MASK) {
             double mk[M];
-            load_vec<M>(mk, p.mask, T, t);
+            load_vec<M>(mk, p.mask, T, t, ok);
 #pragma unroll
             for (int k = 0; k < M; ++k) A[k] = c_scale(A[k], mk[k]);
         }
     } else if (PROG == PROG_LINE_SO_LEN) {
         // P = exp(-i tau (-q z E)) = exp(-i s w_z)   mesh_operators.py:329-341
         double vec[M];
-        load_vec<M>(vec, p.vec, T, t);
+        load_vec<M>(vec, p.vec, T, t, ok);
         cplx ph[M];
         const SinCosBase pbase = sincos_base(sa * vec[0]);
 #pragma unroll
@@ -459,34 +477,34 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
             ph[k] = c_make(cs, -sn);
             A[k] = c_mul(ph[k], A[k]);
         }
-        cn_channel<M>(A, fA, toff, toff_prev, t, T, sm_scan, p.short_scan != 0);
+        cn_channel<M>(A, fA, toff, toff_prev, tl, Tc, sm_scan, short_scan);
 #pragma unroll
         for (int k = 0; k < M; ++k) A[k] = c_mul(ph[k], A[k]);
         if (p.flags & F_MASK) {
             double mk[M];
-            load_vec<M>(mk, p.mask, T, t);
+            load_vec<M>(mk, p.mask, T, t, ok);
 #pragma unroll
             for (int k = 0; k < M; ++k) A[k] = c_scale(A[k], mk[k]);
         }
     } else if (PROG == PROG_LINE_SO_VEL) {
         // theta identical for every z-pair: zvec holds v_pref on rows that start a pair  mesh_operators.py:384-427
         double zv[M];
-        load_vec<M>(zv, p.zvec, T, t);
-        const RPairAngles<M> ang = rpair_angles<M>(zv, p.zprev[t], sa);
+        load_vec<M>(zv, p.zvec, T, t, ok);
+        const RPairAngles<M> ang = rpair_angles<M>(zv, ok ? p.zprev[t] : 0.0, sa);
         rpair_layer_even<M, false>(A, A, ang);
-        rpair_layer_odd<M, false>(A, A, ang, t, T, xs);
-        cn_channel<M>(A, fA, toff, toff_prev, t, T, sm_scan, p.short_scan != 0);
-        rpair_layer_odd<M, false>(A, A, ang, t, T, xs);
+        rpair_layer_odd<M, false>(A, A, ang, tl, Tc, xs);
+        cn_channel<M>(A, fA, toff, toff_prev, tl, Tc, sm_scan, short_scan);
+        rpair_layer_odd<M, false>(A, A, ang, tl, Tc, xs);
         rpair_layer_even<M, false>(A, A, ang);
         if (p.flags & F_MASK) {
             double mk[M];
-            load_vec<M>(mk, p.mask, T, t);
+            load_vec<M>(mk, p.mask, T, t, ok);
 #pragma unroll
             for (int k = 0; k < M; ++k) A[k] = c_scale(A[k], mk[k]);
         }
     }
-    store_rows<M>(A, base, T, t);
-    if (pair) store_rows<M>(B, base + chan, T, t);
+    store_rows<M>(A, base, T, t, mine);
+    if (pair) store_rows<M>(B, base + chan, T, t, mine);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -665,6 +683,7 @@ struct ObserveParams {
     unsigned what;
     double ipm;
     int line;                 // LineMesh: <z> = sum z |g|^2 is the "r" observable; no l coupling
+    int ghost_hi;             // an upper ghost channel follows the last owned channel (l-block shard): <z> couples to it
 };
 
 __global__ void __launch_bounds__(256) k_observe(const ObserveParams p)
@@ -673,7 +692,7 @@ __global__ void __launch_bounds__(256) k_observe(const ObserveParams p)
     const int l = blockIdx.x, b = blockIdx.y;
     const int Rp = p.M * p.T;
     const cplx *row = p.psi + ((size_t)b * p.L + l) * Rp;
-    const bool has_up = (l + 1 < p.L);
+    const bool has_up = (l + 1 < p.L) || p.ghost_hi;
     const bool want_z = (p.what & 16u) && has_up && !p.line && p.cl_z;
     const bool want_h = (p.what & 32u) && p.h_diag;
     double acc[4 + ION_MAX_RADII];

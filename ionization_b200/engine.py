@@ -66,6 +66,9 @@ class DeviceSimulation:
         self.l_begin = int(l_begin)
         self.n_states = 0
         self.n_radii = 0
+        sharded = self.L != self.L_total
+        self.g_lo = 1 if (sharded and self.l_begin > 0) else 0
+        self.g_hi = 1 if (sharded and self.l_begin + self.L < self.L_total) else 0
         nat.check(
             self._lib.ion_sim_create_sharded(self.program, self.L_total, self.l_begin, self.L, self.R, self.batch, self.device, ctypes.byref(self._h)),
             "ion_sim_create",
@@ -94,7 +97,8 @@ class DeviceSimulation:
         nat.check(self._lib.ion_sim_set_stream(self._h, ctypes.c_void_p(cuda_stream)), "ion_sim_set_stream")
 
     def set_hamiltonian(self, h_diag, h_off):
-        h_diag = nat.as_c128(np.asarray(h_diag).reshape(self.L, self.R))
+        """h_diag: [L (+ ghost channels of an l-block shard), R]; h_off: [R-1]"""
+        h_diag = nat.as_c128(np.asarray(h_diag).reshape(self.L + self.g_lo + self.g_hi, self.R))
         h_off = nat.as_f64(h_off)
         if h_off.shape != (self.R - 1,):
             raise exceptions.EngineError(f"h_off must have shape ({self.R - 1},), got {h_off.shape}")
@@ -206,6 +210,26 @@ class DeviceSimulation:
 
     def synchronize(self):
         nat.check(self._lib.ion_sim_synchronize(self._h), "ion_sim_synchronize")
+
+    # -- l-block shards: one step = a few pair-local phases with halo exchanges in between -------
+    @property
+    def num_phases(self) -> int:
+        return int(self._lib.ion_sim_num_phases(self._h))
+
+    def phase_needs_halo(self, phase: int) -> bool:
+        return bool(self._lib.ion_sim_phase_needs_halo(self._h, phase))
+
+    def step_phase(self, phase: int, tau: float, field):
+        field = nat.as_f64(np.broadcast_to(np.asarray(field, dtype=np.float64), (self.batch,)))
+        nat.check(self._lib.ion_sim_step_phase(self._h, phase, float(tau), nat.ptr(field)), "ion_sim_step_phase")
+
+    def halo_buffer(self, which: int):
+        """(device pointer, bytes) of a boundary-channel buffer: 0 send-to-lower, 1 send-to-upper, 2 recv-from-lower,
+        3 recv-from-upper (None when that neighbour does not exist)"""
+        p = ctypes.c_void_p()
+        nbytes = ctypes.c_int64()
+        nat.check(self._lib.ion_sim_halo_buffer(self._h, which, ctypes.byref(p), ctypes.byref(nbytes)), "ion_sim_halo_buffer")
+        return p.value, nbytes.value
 
     # -- measurement ------------------------------------------------------------------------
     @property

@@ -1,0 +1,235 @@
+"""One process per GPU: scan-ensemble sharding and l-block sharding of one large simulation.
+
+* Scan ensembles shard as INDEPENDENT simulations: ``shard_range`` splits the members over the ranks, every rank
+  runs its own batched ``DeviceSimulation`` and there is no data-path collective; results (a few scalars per member)
+  are gathered at the end (``gather_objects``).  The reference does the same with a process pool / HTCondor map
+  (ionization_scans/scan_utils.py:638-663).
+
+* One very large SphericalHarmonicMesh simulation shards over contiguous l-blocks cut at EVEN channels.  The
+  Crank-Nicolson solve (in r) and every even-parity l-pair sweep are local to a shard; only the odd-parity sweeps
+  couple the last channel of one shard to the first channel of the next, so before each odd-parity kernel the two
+  boundary channels are exchanged with NCCL send/recv (1 exchange per step in the length gauge, 3 in the velocity
+  gauge; one channel = R * 16 bytes per direction) and both shards evaluate the straddling pair redundantly.
+  Reductions (norm, inner products, expectation values) are per-shard partial sums + one small all-reduce.
+
+``torch.distributed`` is plumbing only (rendezvous, NCCL p2p, all-reduce); the kernels are the engine's.
+"""
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as nat
+from . import engine as _engine
+from . import exceptions
+
+
+# ---------------------------------------------------------------------------------------------
+# partitioning (pure host logic, tested on CPU)
+# ---------------------------------------------------------------------------------------------
+def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """contiguous block [begin, end) of ``n_items`` for ``rank`` (sizes differ by at most one)"""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, extra = divmod(n_items, world_size)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def l_block_partition(l_total: int, world_size: int) -> List[Tuple[int, int]]:
+    """[(l_begin, L)] per rank: contiguous blocks that begin (and, except the last, end) on EVEN channels, so that
+    only odd-parity pairs (2m+1, 2m+2) straddle a cut."""
+    if l_total % 2:
+        raise exceptions.UnsupportedConfiguration("l-block sharding needs an even l_bound")
+    n_pairs = l_total // 2
+    if world_size > n_pairs:
+        raise exceptions.UnsupportedConfiguration(f"cannot cut {l_total} channels into {world_size} even blocks")
+    out = []
+    for r in range(world_size):
+        b, e = shard_range(n_pairs, r, world_size)
+        out.append((2 * b, 2 * (e - b)))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# device pointers as torch tensors (zero copy) -- for NCCL p2p on the engine's halo buffers
+# ---------------------------------------------------------------------------------------------
+class _CudaArray:
+    def __init__(self, ptr: int, n_float64: int):
+        self.__cuda_array_interface__ = {"shape": (n_float64,), "typestr": "<f8", "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+def device_tensor(ptr: int, nbytes: int, device: int):
+    import torch
+
+    return torch.as_tensor(_CudaArray(ptr, nbytes // 8), device=torch.device("cuda", device))
+
+
+# ---------------------------------------------------------------------------------------------
+# halo exchange
+# ---------------------------------------------------------------------------------------------
+class HaloExchanger:
+    """Exchanges the boundary channels of neighbouring l-block shards with torch.distributed p2p.
+
+    ``send_lo/send_hi/recv_lo/recv_hi`` are torch tensors (views of the engine's halo buffers on CUDA; plain CPU
+    tensors in the gloo tests).  ``exchange()`` posts all sends/receives of the step phase as one batch."""
+
+    def __init__(self, rank: int, world_size: int, send_lo, send_hi, recv_lo, recv_hi, group=None):
+        self.rank, self.world = rank, world_size
+        self.send_lo, self.send_hi, self.recv_lo, self.recv_hi = send_lo, send_hi, recv_lo, recv_hi
+        self.group = group
+
+    def exchange(self):
+        import torch.distributed as dist
+
+        ops = []
+        if self.rank > 0:
+            ops.append(dist.P2POp(dist.isend, self.send_lo, self.rank - 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, self.recv_lo, self.rank - 1, self.group))
+        if self.rank < self.world - 1:
+            ops.append(dist.P2POp(dist.isend, self.send_hi, self.rank + 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, self.recv_hi, self.rank + 1, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+
+class LocalExchanger:
+    """In-process stand-in used to test the shard logic on ONE GPU: all shards live in this process and the
+    'exchange' is a device-to-device copy between their halo buffers."""
+
+    def __init__(self, shards: Sequence["ShardedSimulation"]):
+        self.shards = list(shards)
+
+    def exchange_all(self):
+        for lo, hi in zip(self.shards[:-1], self.shards[1:]):
+            hi.recv_lo.copy_(lo.send_hi)
+            lo.recv_hi.copy_(hi.send_lo)
+
+
+# ---------------------------------------------------------------------------------------------
+# one l-block shard of a SphericalHarmonicMesh simulation
+# ---------------------------------------------------------------------------------------------
+class ShardedSimulation:
+    """The shard of ``problem`` (a dict of hot-path inputs, keys as in tests/golden/*.npz) owned by ``rank``."""
+
+    def __init__(self, problem, rank: int, world_size: int, device: int = 0, use_torch_stream: bool = True):
+        import torch
+
+        kind = str(problem["kind"])
+        if kind not in ("sh_len_so", "sh_vel_so"):
+            raise exceptions.UnsupportedConfiguration("l-block sharding: split-operator SphericalHarmonic programs only")
+        self.rank, self.world, self.device = rank, world_size, device
+        L_total, R = int(problem["L"]), int(problem["R"])
+        self.l_begin, self.L = l_block_partition(L_total, world_size)[rank]
+        self.L_total, self.R = L_total, R
+        eng = _engine.DeviceSimulation(kind, self.L, R, batch=1, device=device, L_total=L_total, l_begin=self.l_begin)
+        self.engine = eng
+        if use_torch_stream:
+            self.stream = torch.cuda.Stream(device=device)
+            eng.set_stream(self.stream.cuda_stream)
+        else:
+            self.stream = None
+        lo, hi = self.l_begin - eng.g_lo, self.l_begin + self.L + eng.g_hi  # channels held, ghosts included
+        eng.set_hamiltonian(np.asarray(problem["h_diag"])[lo:hi], problem["h_off"])
+        if kind == "sh_vel_so":
+            eng.set_vel_coupling(problem["c_l"], problem["f1_l"], problem["y_j"], problem["z_j"])
+        else:
+            eng.set_len_coupling(problem["c_l"], problem["x_j"])
+        eng.set_mask(problem["mask"])
+        sl = np.asarray(problem["state_l"]) if "state_l" in problem else np.zeros(0, dtype=np.int64)
+        rows = problem["state_rows"] if len(sl) else None
+        eng.set_observables(float(problem["delta_r"]), problem["r"], sl, rows, ())
+        eng.write_g(np.asarray(problem["g0"])[self.l_begin : self.l_begin + self.L].reshape(1, self.L, R))
+        bufs = [eng.halo_buffer(w) for w in range(4)]
+        mk = lambda pb: None if pb[0] is None else device_tensor(pb[0], pb[1], device)
+        self.send_lo, self.send_hi, self.recv_lo, self.recv_hi = (mk(b) for b in bufs)
+        self.n_phases = eng.num_phases
+        self.halo_phases = [p for p in range(self.n_phases) if eng.phase_needs_halo(p)]
+
+    def make_exchanger(self, group=None) -> HaloExchanger:
+        return HaloExchanger(self.rank, self.world, self.send_lo, self.send_hi, self.recv_lo, self.recv_hi, group)
+
+    def close(self):
+        self.engine.close()
+
+    # ---- stepping -----------------------------------------------------------------------------
+    def run_phase(self, phase: int, tau: float, field: float):
+        self.engine.step_phase(phase, tau, field)
+
+    def step(self, taus, fields, exchanger: Optional[HaloExchanger] = None):
+        """advance len(taus) steps; with ``exchanger`` (torch.distributed) the halos are exchanged before every
+        odd-parity phase.  Every rank must call this collectively."""
+        import torch
+
+        taus = np.atleast_1d(taus)
+        fields = np.atleast_1d(fields)
+        ctx = torch.cuda.stream(self.stream) if self.stream is not None else _NullCtx()
+        with ctx:
+            for tau, f in zip(taus, fields):
+                for ph in range(self.n_phases):
+                    if exchanger is not None and ph in self.halo_phases:
+                        exchanger.exchange()
+                    self.engine.step_phase(ph, float(tau), float(f))
+
+    # ---- observables ---------------------------------------------------------------------------
+    def partial_observation(self, what: int, exchanger: Optional[HaloExchanger] = None):
+        """this shard's contribution to the observation record (sums over owned channels; <z> also couples the last
+        owned channel to the upper ghost, which must be current: the halos are refreshed first)"""
+        if exchanger is not None and (what & nat.OBS_Z):
+            exchanger.exchange()
+        return self.engine.observe(what)[0]
+
+    def read_g(self):
+        return self.engine.read_g()[0]
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def combine_observations(records: Sequence[np.ndarray], what: int, n_states: int, l_counts: Sequence[int], n_radii: int = 0):
+    """merge per-shard records into the record of the whole simulation: scalars add, norm_by_l concatenates"""
+    out = []
+    c = [0] * len(records)
+
+    def take(k):
+        vals = [r[c[i] : c[i] + (k[i] if isinstance(k, (list, tuple)) else k)] for i, r in enumerate(records)]
+        for i in range(len(records)):
+            c[i] += k[i] if isinstance(k, (list, tuple)) else k
+        return vals
+
+    if what & nat.OBS_NORM:
+        out.append(np.sum(take(1), axis=0))
+    if what & nat.OBS_INNER_PRODUCTS:
+        out.append(np.sum(take(2 * n_states), axis=0))
+    if what & nat.OBS_NORM_BY_L:
+        out.append(np.concatenate(take(list(l_counts))))
+    for bit in (nat.OBS_R, nat.OBS_Z, nat.OBS_H0):
+        if what & bit:
+            out.append(np.sum(take(1), axis=0))
+    if what & nat.OBS_NORM_WITHIN:
+        out.append(np.sum(take(n_radii), axis=0))
+    return np.concatenate(out)
+
+
+def all_reduce_observation(record: np.ndarray, device: int, group=None) -> np.ndarray:
+    """sum of the additive part of an observation record over the ranks (NCCL all-reduce of a few doubles)"""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.from_numpy(np.ascontiguousarray(record)).to(torch.device("cuda", device) if dist.get_backend(group) == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
+
+
+def gather_objects(obj, group=None):
+    """gather small python objects (per-member result dictionaries of an ensemble shard) on every rank"""
+    import torch.distributed as dist
+
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, obj, group=group)
+    return out

@@ -1,0 +1,125 @@
+"""GPU tests of (1) l-block sharding -- several shards on ONE GPU with an in-process halo exchange must reproduce the
+unsharded run and the reference fixture -- and (2) r-segmented kernels (r_points > 4096) against the oracle."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _run_sharded(p, world, n_steps=None, what=0):
+    from ionization_b200 import parallel
+
+    shards = [parallel.ShardedSimulation(p, r, world, device=0, use_torch_stream=False) for r in range(world)]
+    ex = parallel.LocalExchanger(shards)
+    taus, fields = p["taus"][:n_steps], p["fields"][:n_steps]
+    import torch
+
+    for tau, f in zip(taus, fields):
+        for ph in range(shards[0].n_phases):
+            if ph in shards[0].halo_phases:
+                for s in shards:
+                    s.engine.synchronize()
+                ex.exchange_all()
+                torch.cuda.synchronize()
+            for s in shards:
+                s.run_phase(ph, tau, f)
+    for s in shards:
+        s.engine.synchronize()
+    g = np.concatenate([s.read_g() for s in shards], axis=0)
+    rec = None
+    if what:
+        ex.exchange_all()
+        torch.cuda.synchronize()
+        recs = [s.partial_observation(what) for s in shards]
+        rec = parallel.combine_observations(recs, what, n_states=len(p["state_l"]), l_counts=[s.L for s in shards])
+    for s in shards:
+        s.close()
+    return g, rec
+
+
+@pytest.mark.parametrize("name", ["sh_len_so_100x10", "sh_vel_so_60x8", "sh_len_so_datastores_120x12", "sh_vel_so_datastores_120x12"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_l_block_shards_reproduce_reference(name, world):
+    from ionization_b200 import _native as nat
+
+    p = load_golden(name)
+    what = nat.OBS_NORM | nat.OBS_INNER_PRODUCTS | nat.OBS_NORM_BY_L | nat.OBS_R | nat.OBS_Z | nat.OBS_H0
+    g, rec = _run_sharded(p, world, what=what)
+    assert rel_err(g, p["g_final"]) < TOL
+    ns = len(p["state_l"])
+    assert abs(rec[0] - p["norm"][-1]) < TOL
+    ips = rec[1 : 1 + 2 * ns].reshape(ns, 2)
+    assert np.max(np.abs(ips[:, 0] + 1j * ips[:, 1] - p["inner_products"][-1])) < TOL
+    if "norm_by_l" in p:
+        L = int(p["L"])
+        c = 1 + 2 * ns
+        assert np.max(np.abs(rec[c : c + L] - p["norm_by_l"][-1])) < TOL
+        assert abs(rec[c + L] - p["r_expectation"][-1]) < TOL * abs(p["r_expectation"][-1])
+        assert abs(rec[c + L + 1] - p["z_expectation"][-1]) < TOL * abs(p["r_expectation"][-1])
+        assert abs(rec[c + L + 2] - p["internal_energy"][-1]) < TOL * abs(p["internal_energy"][-1])
+
+
+@pytest.mark.parametrize("kind", ["LEN", "VEL"])
+def test_l_block_shards_equal_unsharded_run_on_a_larger_mesh(kind):
+    from ionization_b200 import configs, engine
+    from ionization_b200 import units as u
+
+    p = configs.spherical_harmonic_problem(r_bound=60 * u.bohr_radius, r_points=600, l_bound=64, gauge=kind, n_steps=40,
+                                           pulse=configs.sinc_pulse(20 * u.asec, 5 * u.Jcm2), time_initial=-20 * u.asec, time_final=20 * u.asec)
+    with engine.DeviceSimulation.from_problem(p) as sim:
+        sim.step(p["taus"], p["fields"])
+        g_ref = sim.read_g()[0]
+    g, _ = _run_sharded(p, 4)
+    assert rel_err(g, g_ref) < 1e-12
+
+
+@pytest.mark.parametrize("kind", ["LEN", "VEL"])
+@pytest.mark.parametrize("R", [5000, 4609])
+def test_r_segmented_kernels_match_oracle(kind, R):
+    """r_points > 4096: every channel is processed by several CTAs with recomputed halos (kernels.cuh)"""
+    from ionization_b200 import configs, engine
+    from ionization_b200 import units as u
+    from oracle import cport
+
+    p = configs.spherical_harmonic_problem(r_bound=0.1 * R * u.bohr_radius, r_points=R, l_bound=6, gauge=kind, n_steps=30,
+                                           pulse=configs.sinc_pulse(20 * u.asec, 5 * u.Jcm2), time_initial=-15 * u.asec, time_final=15 * u.asec)
+    # spread the wavefunction over the whole radial range so that every segment boundary carries amplitude
+    rng = np.random.default_rng(R)
+    g0 = (rng.standard_normal((6, R)) + 1j * rng.standard_normal((6, R))) * np.exp(-((p["r"] / p["r"][-1]) ** 2))[None, :]
+    p["g0"] = g0 / np.sqrt(np.sum(np.abs(g0) ** 2) * float(p["delta_r"]))
+    ref = cport.sh_steps(p)
+    with engine.DeviceSimulation.from_problem(p) as sim:
+        sim.step(p["taus"], p["fields"])
+        g = sim.read_g()[0]
+        norm = sim.observe(engine.nat.OBS_NORM)[0, 0]
+    assert rel_err(g, ref) < TOL
+    assert abs(norm - np.sum(np.abs(ref) ** 2) * float(p["delta_r"])) < TOL
+
+
+def test_segmented_line_split_operator_long_mesh():
+    """LineMesh with 2^14 points (SO, both gauges) against the C oracle"""
+    from ionization_b200 import engine
+    from oracle import cport
+
+    for kind in ("line_len_so", "line_vel_so"):
+        p = dict(load_golden(f"{kind}_1024"))
+        Z = 2 ** 14
+        z = np.linspace(-1, 1, Z) * p["z"][-1] * 16
+        dz = z[1] - z[0]
+        scale = (float(p["delta_z"]) / dz) ** 2
+        p.update(Z=Z, z=z, delta_z=dz, h_off=np.full(Z - 1, p["h_off"][0] * scale), w_z=z * (p["w_z"][-1] / p["z"][-1]), mask=np.ones(Z),
+                 v_pref=float(p["v_pref"]) * float(p["delta_z"]) / dz)
+        p["h_diag"] = np.full(Z, -2 * p["h_off"][0]) + 0j + np.interp(z, load_golden(f"{kind}_1024")["z"], np.real(load_golden(f"{kind}_1024")["h_diag"]) + 2 * load_golden(f"{kind}_1024")["h_off"][0])
+        rng = np.random.default_rng(1)
+        g0 = (rng.standard_normal(Z) + 1j * rng.standard_normal(Z)) * np.exp(-((z / z[-1]) ** 2) * 2)
+        p["g0"] = g0 / np.sqrt(np.sum(np.abs(g0) ** 2) * dz)
+        p["state_rows"] = p["g0"][None, :]
+        p["fields"] = p["fields"] * 0.05
+        ref = cport.line_steps(p)
+        with engine.DeviceSimulation.from_problem(p) as sim:
+            sim.step(p["taus"], p["fields"])
+            g = sim.read_g()[0, 0]
+        assert rel_err(g, ref) < TOL, kind
