@@ -136,6 +136,50 @@ ION_DEVINL cplx affine_scan_block_exclusive(cplx P, cplx B, cplx *smP, cplx *smB
     return first ? win : c_fma(Pe, win, Be);
 }
 
+// ---------------------------------------------------------------------------------------------
+// 2x2 complex matrices acting projectively on a pivot p = n/d: the Thomas pivot recurrence
+// p_i = D_i + o^2 / p_{i-1} is the Moebius map [[D_i, o^2], [1, 0]].  Products are rescaled by a power of two
+// (pivots have modulus > 1, so unnormalised products overflow after a few hundred rows).
+// ---------------------------------------------------------------------------------------------
+struct Mat2 {
+    cplx a, b, c, d;
+};
+ION_DEVINL Mat2 mat_mul(const Mat2 &L, const Mat2 &R)  // L * R  (R acts first)
+{
+    Mat2 o;
+    o.a = c_fma(L.b, R.c, c_mul(L.a, R.a));
+    o.b = c_fma(L.b, R.d, c_mul(L.a, R.b));
+    o.c = c_fma(L.d, R.c, c_mul(L.c, R.a));
+    o.d = c_fma(L.d, R.d, c_mul(L.c, R.b));
+    return o;
+}
+ION_DEVINL void mat_normalize(Mat2 &m)
+{
+    double mx = fmax(fmax(fmax(fabs(m.a.x), fabs(m.a.y)), fmax(fabs(m.b.x), fabs(m.b.y))),
+                     fmax(fmax(fabs(m.c.x), fabs(m.c.y)), fmax(fabs(m.d.x), fabs(m.d.y))));
+    int e = ((__double2hiint(mx) >> 20) & 0x7ff) - 1023;      // floor(log2(mx)) for normal numbers
+    e = max(-1000, min(1000, e));
+    const double sc = __hiloint2double((1023 - e) << 20, 0);  // 2^-e, exact
+    m.a = c_scale(m.a, sc);
+    m.b = c_scale(m.b, sc);
+    m.c = c_scale(m.c, sc);
+    m.d = c_scale(m.d, sc);
+}
+ION_DEVINL Mat2 mat_shfl_up(const Mat2 &m, int d)
+{
+    Mat2 o;
+    o.a = shfl_up_c(m.a, d);
+    o.b = shfl_up_c(m.b, d);
+    o.c = shfl_up_c(m.c, d);
+    o.d = shfl_up_c(m.d, d);
+    return o;
+}
+ION_DEVINL cplx c_div(cplx n, cplx d)
+{
+    const double s = 1.0 / c_abs2(d);
+    return make_double2((n.x * d.x + n.y * d.y) * s, (n.y * d.x - n.x * d.y) * s);
+}
+
 // block-wide sum of NV doubles; result valid in thread 0.  sm: >= 32*NV doubles.
 template <int NV>
 ION_DEVINL void block_sum(double (&v)[NV], double *sm, int tid, int nthreads)

@@ -90,7 +90,7 @@ struct ion_sim {
     cplx *h_diag = nullptr;
     double *h_off = nullptr;
     std::vector<double> h_off_host;
-    cplx *w = nullptr, *aggP = nullptr, *aggQ = nullptr;
+    cplx *w = nullptr, *aggP = nullptr, *aggQ = nullptr, *th = nullptr;
     double *toff = nullptr, *toff_prev = nullptr;
     double *vec = nullptr, *zvec = nullptr, *zprev = nullptr, *mask = nullptr, *rvec = nullptr;
     double *cl = nullptr, *cl2 = nullptr, *cl_z = nullptr;
@@ -139,6 +139,7 @@ struct ion_sim {
             if (p) cudaFree(p);
         if (scal_chunk) cudaFree(scal_chunk);
         if (scal_phase) cudaFree(scal_phase);
+        if (th) cudaFree(th);
         if (obs_chunk) cudaFree(obs_chunk);
         for (auto &g : graphs)
             if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
@@ -239,7 +240,7 @@ int prepare_kernels(ion_sim *s)
     if ((rc = set_unit_smem_attr<ion::PROG_ROT>()) || (rc = set_unit_smem_attr<ion::PROG_ROT_CN_ROT>()) ||
         (rc = set_unit_smem_attr<ion::PROG_H2>()) || (rc = set_unit_smem_attr<ion::PROG_H2_CN_H2>()) ||
         (rc = set_unit_smem_attr<ion::PROG_CN>()) || (rc = set_unit_smem_attr<ion::PROG_LINE_SO_LEN>()) ||
-        (rc = set_unit_smem_attr<ion::PROG_LINE_SO_VEL>()))
+        (rc = set_unit_smem_attr<ion::PROG_LINE_SO_VEL>()) || (rc = set_unit_smem_attr<ion::PROG_LINE_CN>()))
         return rc;
     return ION_OK;
 }
@@ -252,6 +253,7 @@ ion::UnitParams base_params(ion_sim *s)
     p.w = s->w;
     p.aggP = s->aggP;
     p.aggQ = s->aggQ;
+    p.th = s->th;
     p.toff = s->toff;
     p.toff_prev = s->toff_prev;
     p.vec = s->vec;
@@ -283,7 +285,8 @@ int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, c
     switch (prog) {
         case ion::PROG_CN:
         case ion::PROG_LINE_SO_LEN:
-        case ion::PROG_LINE_SO_VEL: units = s->L; break;
+        case ion::PROG_LINE_SO_VEL:
+        case ion::PROG_LINE_CN: units = s->L; break;
         default: units = ion::num_units(s->L, s->l_begin, parity);
     }
     dim3 grid(units * s->S, s->batch);
@@ -324,6 +327,11 @@ int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, c
             kind = KK_LINE_SO_VEL;
             prof_begin(s, kind);
             rc = launch_unit_prog<ion::PROG_LINE_SO_VEL>(s, p, grid);
+            break;
+        case ion::PROG_LINE_CN:
+            kind = KK_LINE_CN;
+            prof_begin(s, kind);
+            rc = launch_unit_prog<ion::PROG_LINE_CN>(s, p, grid);
             break;
         default: return fail(ION_EINVAL, "unknown unit program");
     }
@@ -406,6 +414,15 @@ int ensure_factor(ion_sim *s, double tau)
                 mx = std::max(mx, hb[(size_t)l * nw + w]);
             }
         s->short_scan = (nw > 1) && (mx < std::log(1e-30));
+        if (s->program == ION_LINE_LEN_CN) {
+            if (s->T / 32 > 1 && !s->short_scan)
+                return fail(ION_ENOTSUP,
+                            "LineMesh Crank-Nicolson rebuilds its pivots per warp and needs the LU multipliers to decay below 1e-30 "
+                            "over 128 rows; this time step is too large for the mesh spacing");
+            if (int rc = dev_alloc(&s->th, (size_t)s->Rp)) return rc;
+            ion::k_make_th<<<(s->Rp + 127) / 128, 128, 0, s->stream>>>(s->h_diag, tau, s->R, s->M, s->T, s->th);
+            CUDA_TRY(cudaGetLastError());
+        }
         if (s->S > 1 && !s->short_scan)
             return fail(ION_ENOTSUP,
                         "r_points > 4096 needs the Crank-Nicolson LU multipliers to decay below 1e-30 over 128 rows; this time "
@@ -461,6 +478,7 @@ int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, bool pre_d
         }
         case ION_LINE_LEN_SO: return launch_unit(s, PROG_LINE_SO_LEN, 0, F_MASK, sa, nullptr);
         case ION_LINE_VEL_SO: return launch_unit(s, PROG_LINE_SO_VEL, 0, F_MASK, sa, nullptr);
+        case ION_LINE_LEN_CN: return launch_unit(s, PROG_LINE_CN, 0, F_MASK, sa, nullptr);
         default: return fail(ION_ENOTSUP, "program not supported by this build");
     }
 }
@@ -768,7 +786,6 @@ int ion_sim_create_sharded(int program, int64_t L_total, int64_t l_begin, int64_
     if (program < 0 || program > ION_SH_LEN_ADI) return fail(ION_EINVAL, "unknown program");
     if (line && L_total != 1) return fail(ION_EINVAL, "LineMesh programs need L = 1");
     if (program == ION_SH_LEN_ADI) return fail(ION_ENOTSUP, "ION_SH_LEN_ADI is not implemented in this build");
-    if (program == ION_LINE_LEN_CN) return fail(ION_ENOTSUP, "ION_LINE_LEN_CN is not implemented in this build");
     const bool sharded = (L != L_total);
     if (sharded) {
         if (batch != 1) return fail(ION_ENOTSUP, "l-block shards hold one simulation (batch = 1)");

@@ -38,6 +38,7 @@ struct UnitParams {
     const double *mask;      // [M][T] or nullptr
     const double *cl;        // [L_total-1] l-pair coefficient for rotations (c_l or c_l*(l+1)), GLOBAL l
     const double *cl2;       // [L_total-1] l-pair coefficient for the r-pair rotations
+    const cplx *th;          // [M][T]      tau * h_diag of a LineMesh (time-dependent Crank-Nicolson, PROG_LINE_CN)
     const double *scal_a;    // [batch] per-simulation scalar s = tau*field of this step (or nullptr = 0)
     const double *scal_b;    // [batch] second scalar fused in (next step's), or nullptr
     int L;                   // channels held in psi (owned + ghost channels of an l-block shard)
@@ -334,7 +335,82 @@ enum : int {
     PROG_CN = 4,         // CN on every channel (unit = channel)                    -- generic path
     PROG_LINE_SO_LEN = 5,// exp(-i s w_z) * CN * exp(-i s w_z) [+ mask]             -- LineMesh SO length gauge
     PROG_LINE_SO_VEL = 6,// r-pair rotations even, odd, CN, odd, even [+ mask]      -- LineMesh SO velocity gauge
+    PROG_LINE_CN = 7,    // CN with H = H0 + diag(s w_z): pivots rebuilt every step     -- LineMesh CN (ADI) length gauge
 };
+
+// ---------------------------------------------------------------------------------------------
+// LU factors of (1 + i tau (H0 + diag(E w_z))) built on the fly (LineMesh Crank-Nicolson in the length gauge:
+// evolution_methods.py:49-77 with mesh_operators.py:271-298, :320-327 -- the matrix changes every step and differs
+// between the members of an ensemble, so nothing can be precomputed).  The pivot recurrence is a Moebius map per row;
+// each thread composes the maps of its M rows, a Kogge-Stone scan of 2x2 matrices over the warp gives every lane the
+// pivot entering its chunk, and the thread then rebuilds its M pivots.  Across warps only the neighbour's last pivot
+// is needed: a pivot forgets its starting value at the rate |o/p|^2 per row (< 1e-30 over a warp; the host checks the
+// same decay bound as for r-segments before it accepts this program).
+// ---------------------------------------------------------------------------------------------
+template <int M>
+ION_DEVINL void line_cn_factors(CnFactors<M> &f, const cplx (&D)[M], const double (&toff)[M], double toff_prev, int tl, cplx *sm)
+{
+    const int lane = tl & 31, warp = tl >> 5;
+    double o2[M];
+    o2[0] = toff_prev * toff_prev;
+#pragma unroll
+    for (int k = 1; k < M; ++k) o2[k] = toff[k - 1] * toff[k - 1];
+    Mat2 X;
+    X.a = D[0];
+    X.b = c_make(o2[0], 0.0);
+    X.c = c_make(1.0, 0.0);
+    X.d = c_zero();
+#pragma unroll
+    for (int k = 1; k < M; ++k) {
+        Mat2 Y;
+        Y.a = c_make(fma(o2[k], X.c.x, fma(D[k].x, X.a.x, -D[k].y * X.a.y)), fma(o2[k], X.c.y, fma(D[k].x, X.a.y, D[k].y * X.a.x)));
+        Y.b = c_make(fma(o2[k], X.d.x, fma(D[k].x, X.b.x, -D[k].y * X.b.y)), fma(o2[k], X.d.y, fma(D[k].x, X.b.y, D[k].y * X.b.x)));
+        Y.c = X.a;
+        Y.d = X.b;
+        X = Y;
+    }
+    mat_normalize(X);
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        Mat2 Y = mat_shfl_up(X, s);
+        if (lane >= s) {
+            X = mat_mul(X, Y);
+            mat_normalize(X);
+        }
+    }
+    // last pivot of this warp when nothing precedes it (start value "infinity" = (1, 0)): n/d = a/c
+    if (lane == 31) sm[warp] = c_div(X.a, X.c);
+    __syncthreads();
+    const bool inf_in = (warp == 0);
+    const cplx pin_warp = inf_in ? c_zero() : sm[warp - 1];
+    Mat2 Y = mat_shfl_up(X, 1);
+    cplx wprev;  // 1 / (pivot of the row before this thread's first row); 0 when there is none
+    if (lane == 0) {
+        wprev = inf_in ? c_zero() : c_inv(pin_warp);
+    } else {
+        cplx n = inf_in ? Y.a : c_fma(Y.a, pin_warp, Y.b);
+        cplx d = inf_in ? Y.c : c_fma(Y.c, pin_warp, Y.d);
+        wprev = c_div(d, n);
+    }
+    f.wprev = wprev;
+    cplx wp = wprev;
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        cplx piv = c_make(fma(o2[k], wp.x, D[k].x), fma(o2[k], wp.y, D[k].y));
+        wp = c_inv(piv);
+        f.w[k] = wp;
+    }
+    // chunk aggregates of the affine recurrences (k_aggregates, on the fly)
+    cplx P = c_make(toff_prev * wprev.y, -toff_prev * wprev.x), Q = c_make(1.0, 0.0);
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        cplx e = c_make(toff[k] * f.w[k].y, -toff[k] * f.w[k].x);
+        if (k < M - 1) P = c_mul(P, e);
+        Q = c_mul(Q, e);
+    }
+    f.P = P;
+    f.Q = Q;
+}
 
 // register budget: the programs without a Crank-Nicolson solve are asked to fit two CTAs of TMAX threads per SM
 // (<= 64 registers at TMAX = 512) so that one CTA's loads overlap the other's arithmetic
@@ -361,7 +437,7 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
     const int b = blockIdx.y;
     int l0;
     bool pair = true;
-    if (PROG == PROG_CN || PROG == PROG_LINE_SO_LEN || PROG == PROG_LINE_SO_VEL) {
+    if (PROG == PROG_CN || PROG == PROG_LINE_SO_LEN || PROG == PROG_LINE_SO_VEL || PROG == PROG_LINE_CN) {
         l0 = unit;
         pair = false;
     } else {
@@ -421,7 +497,7 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
     load_rows<M>(A, base, T, t, ok);
     if (pair) load_rows<M>(B, base + chan, T, t, ok);
     CnFactors<M> fA, fB;
-    {
+    if (PROG != PROG_LINE_CN) {
         const bool single_channel_prog = (PROG == PROG_LINE_SO_LEN || PROG == PROG_LINE_SO_VEL);
         const size_t lw = single_channel_prog ? 0 : (size_t)l0;
         cn_load<M>(fA, p.w + lw * chan, p.aggP + lw * T, p.aggQ + lw * T, t, T, ok);
@@ -480,6 +556,23 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         cn_channel<M>(A, fA, toff, toff_prev, tl, Tc, sm_scan, short_scan);
 #pragma unroll
         for (int k = 0; k < M; ++k) A[k] = c_mul(ph[k], A[k]);
+        if (p.flags & F_MASK) {
+            double mk[M];
+            load_vec<M>(mk, p.mask, T, t, ok);
+#pragma unroll
+            for (int k = 0; k < M; ++k) A[k] = c_scale(A[k], mk[k]);
+        }
+    } else if (PROG == PROG_LINE_CN) {
+        double wz[M];
+        load_vec<M>(wz, p.vec, T, t, ok);
+        cplx D[M];
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+            cplx th = ok ? ld_c(p.th + (size_t)k * T + t) : c_zero();
+            D[k] = c_make(1.0 - th.y, fma(sa, wz[k], th.x));  // 1 + i (tau h + tau E w_z)
+        }
+        line_cn_factors<M>(fA, D, toff, toff_prev, tl, xs);
+        cn_channel<M>(A, fA, toff, toff_prev, tl, Tc, sm_scan, true);
         if (p.flags & F_MASK) {
             double mk[M];
             load_vec<M>(mk, p.mask, T, t, ok);
@@ -617,6 +710,16 @@ __global__ void k_aggregates(const cplx *__restrict__ w, const double *__restric
     }
     aggP[(size_t)l * T + t] = P;
     aggQ[(size_t)l * T + t] = Q;
+}
+
+// tau * h_diag of a single channel, permuted (PROG_LINE_CN)
+__global__ void k_make_th(const cplx *__restrict__ h_diag, double tau, int R, int M, int T, cplx *__restrict__ th)
+{
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= M * T) return;
+    const int k = pos / T, t = pos % T;
+    const long long i = (long long)t * M + k;
+    th[pos] = (i < R) ? c_scale(h_diag[i], tau) : c_zero();
 }
 
 // log-magnitude of the product of the chunk multipliers over each warp (32 consecutive threads): the host takes

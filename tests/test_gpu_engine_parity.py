@@ -164,14 +164,50 @@ def test_known_answers_of_the_reference(name):
     assert rel_err(g, p["g_final"]) < TOL
 
 
-@pytest.mark.parametrize("name", ["line_len_so_1024", "line_len_so_1023", "line_vel_so_1024", "line_vel_so_1023"])
-def test_line_split_operator(name):
+@pytest.mark.parametrize("name", ["line_len_so_1024", "line_len_so_1023", "line_vel_so_1024", "line_vel_so_1023", "line_len_cn_1024", "line_len_cn_1023"])
+def test_line_mesh_programs(name):
     eng = _engine()
     p = load_golden(name)
     with eng.DeviceSimulation.from_problem(p) as sim:
         sim.step(p["taus"], p["fields"])
         g = sim.read_g()[0, 0]
     assert rel_err(g, p["g_final"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["known_line_len_cn_4096", "known_line_len_so_4096", "known_line_vel_so_4096"])
+def test_line_known_answers_of_the_reference(name):
+    """dev/meshes/mesh_refactoring_helper.py:40-63,:204-251: QHO driven by a sine wave, 4096 points, 1000 steps; final
+    initial-state overlaps 0.370010185740 (LEN CN), 0.370008474418 (LEN SO), 0.370924310122 (VEL SO)"""
+    eng = _engine()
+    p = load_golden(name)
+    expected = {"known_line_len_cn_4096": 0.370010185740, "known_line_len_so_4096": 0.370008474418, "known_line_vel_so_4096": 0.370924310122}[name]
+    what = eng.nat.OBS_NORM | eng.nat.OBS_INNER_PRODUCTS
+    with eng.DeviceSimulation.from_problem(p) as sim:
+        sim.step(p["taus"], p["fields"])
+        rec = sim.observe(what)[0]
+        g = sim.read_g()[0, 0]
+    ns = len(p["state_rows"])
+    ips = rec[1 : 1 + 2 * ns].reshape(ns, 2)
+    overlap = abs(ips[int(p["initial_state_index"]), 0] + 1j * ips[int(p["initial_state_index"]), 1]) ** 2
+    assert abs(overlap - expected) < 5e-12
+    assert rel_err(g, p["g_final"]) < TOL
+
+
+def test_line_cn_ensemble_with_different_fields():
+    """config 2 shape: a batch of LineMesh CN simulations with different pulses; every member has its own matrix"""
+    eng = _engine()
+    from oracle import cport
+
+    p = load_golden("line_len_cn_1024")
+    scales = np.array([1.0, -0.5, 3.0, 0.0, 10.0])
+    fields = p["fields"][:, None] * scales[None, :]
+    with eng.DeviceSimulation.from_problem(p, batch=len(scales)) as sim:
+        sim.step(p["taus"], fields)
+        gb = sim.read_g()[:, 0, :]
+    assert rel_err(gb[0], p["g_final"]) < TOL
+    g0 = np.repeat(np.asarray(p["g0"])[None, :], len(scales), axis=0)
+    ref = cport.line_steps(p, g=g0, fields=fields)
+    assert rel_err(gb, ref) < TOL
 
 
 def test_ensemble_batch_matches_independent_runs():

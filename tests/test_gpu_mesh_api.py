@@ -86,7 +86,7 @@ def test_all_datastores_through_the_api():
     assert np.max(np.abs(sim.data.vector_potential_amplitude - ref["vector_potential_amplitude"])) < 1e-12 * np.max(np.abs(ref["vector_potential_amplitude"]))
 
 
-@pytest.mark.parametrize("kind", ["line_len_so", "line_vel_so"])
+@pytest.mark.parametrize("kind", ["line_len_so", "line_vel_so", "line_len_cn"])
 @pytest.mark.parametrize("Z", [1024, 1023])
 def test_line_simulation_matches_reference(kind, Z):
     ref = load_golden(f"{kind}_{Z}")
@@ -97,7 +97,7 @@ def test_line_simulation_matches_reference(kind, Z):
         "line", z_bound=zb, z_points=Z, test_mass=u.electron_mass, internal_potential=well, initial_state=S.GaussianWellState.from_potential(well, u.electron_mass),
         electric_potential=P.SincPulse(pulse_width=100 * u.asec, fluence=0.1 * u.Jcm2, phase=0.3), time_initial=-25 * u.asec, time_final=25 * u.asec,
         time_step=1 * u.asec, mask=P.RadialCosineMask(inner_radius=0.8 * zb, outer_radius=zb, smoothness=8), operators=ops,
-        evolution_method=ion.mesh.SplitInteractionOperator(),
+        evolution_method=ion.mesh.AlternatingDirectionImplicit() if kind == "line_len_cn" else ion.mesh.SplitInteractionOperator(),
     ).to_sim()
     sim.run()
     assert rel_err(sim.mesh.g, ref["g_final"]) < TOL

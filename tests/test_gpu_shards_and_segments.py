@@ -100,14 +100,13 @@ def test_r_segmented_kernels_match_oracle(kind, R):
 
 
 def test_segmented_line_split_operator_long_mesh():
-    """LineMesh with 2^14 points (SO, both gauges) against the C oracle"""
+    """LineMesh with 2^14 / 2^16 points (SO both gauges, CN) against the C oracle"""
     from ionization_b200 import engine
     from oracle import cport
 
-    for kind in ("line_len_so", "line_vel_so"):
+    for kind, Z in (("line_len_so", 2 ** 14), ("line_vel_so", 2 ** 14), ("line_len_cn", 2 ** 14), ("line_len_cn", 2 ** 16)):
         p = dict(load_golden(f"{kind}_1024"))
-        Z = 2 ** 14
-        z = np.linspace(-1, 1, Z) * p["z"][-1] * 16
+        z = np.linspace(-1, 1, Z) * p["z"][-1] * (Z // 1024)
         dz = z[1] - z[0]
         scale = (float(p["delta_z"]) / dz) ** 2
         p.update(Z=Z, z=z, delta_z=dz, h_off=np.full(Z - 1, p["h_off"][0] * scale), w_z=z * (p["w_z"][-1] / p["z"][-1]), mask=np.ones(Z),
