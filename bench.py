@@ -48,8 +48,18 @@ def measured_peak_gbs():
 
 
 def build_workload(name):
+    """-> (problem, description[, batch, fields[n_steps, batch]])"""
     from ionization_b200 import configs
 
+    if name == "c4_len_ensemble":
+        # configs[3] per GPU: 512 members of the 64 x 64 fluence x CEP scan on r_points=1000, l_bound=200
+        p = configs.config4_member("LEN")
+        fields = configs.scan_fields(p, np.geomspace(0.01, 20, 16), np.linspace(0, 2 * np.pi, 32, endpoint=False))
+        return p, "configs[3] (one GPU's share): 512-member fluence x CEP scan, SphericalHarmonicMesh r_points=1000 l_bound=200 length gauge split-operator, 2000 steps", 512, fields
+    if name == "c2_line_ensemble":
+        p = configs.config2(n_steps=1000)
+        fields = configs.scan_fields(p, np.geomspace(0.01, 10, 32), np.linspace(0, 2 * np.pi, 32, endpoint=False))
+        return p, "configs[1]: LineMesh Gaussian well 2^16 points Crank-Nicolson length gauge, batch of 1024 Sinc pulses, 1000 steps", 1024, fields
     if name == "c3_vel":
         return configs.config3("VEL"), "configs[2]: SphericalHarmonicMesh hydrogen 1s r_bound=250a0 r_points=2000 l_bound=500 velocity gauge split-operator, Sinc 200as, 2000 steps, single sim"
     if name == "c3_len":
@@ -109,44 +119,63 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_rate(problem, seconds_target, min_steps=2, max_steps=400):
-    """updates/s of the oracle C port on a bounded sample (first n time steps of the workload)"""
+def cpu_steps(problem, n, members=1):
+    """n time steps of the workload on the CPU port; returns grid-point updates done"""
     from oracle import cport
 
-    L, R = int(problem["L"]), int(problem["R"])
+    if str(problem["kind"]).startswith("line"):
+        Z = int(problem["Z"])
+        g = np.repeat(np.asarray(problem["g0"], dtype=np.complex128).reshape(1, Z), members, axis=0)
+        f = np.repeat(np.asarray(problem["fields"][:n]).reshape(n, 1), members, axis=1)
+        cport.line_steps(problem, g=g, fields=f, nsteps=n)
+        return n * Z * members
+    cport.sh_steps(problem, nsteps=n)
+    return n * int(problem["L"]) * int(problem["R"])
+
+
+def cpu_reference_rate(problem, seconds_target, min_steps=2, max_steps=400):
+    """updates/s of the oracle C port on a bounded sample (first n time steps of the workload; LineMesh: one member per
+    host thread, as the reference's process pool would run an ensemble)"""
+    from oracle import cport
+
+    members = cport.num_threads() if str(problem["kind"]).startswith("line") else 1
     t0 = time.perf_counter()
-    cport.sh_steps(problem, nsteps=1)
+    cpu_steps(problem, 1, members)
     t1 = time.perf_counter() - t0
     n = int(max(min_steps, min(max_steps, seconds_target / max(t1, 1e-6))))
     t0 = time.perf_counter()
-    cport.sh_steps(problem, nsteps=n)
+    upd = cpu_steps(problem, n, members)
     dt = time.perf_counter() - t0
-    return n * L * R / dt, n, dt, cport.num_threads()
+    return upd / dt, n, dt, cport.num_threads()
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    problem, desc = build_workload(args.workload)
+    wl = build_workload(args.workload)
+    problem, desc = wl[0], wl[1]
     from oracle import cport
 
-    L, R = int(problem["L"]), int(problem["R"])
+    is_line = str(problem["kind"]).startswith("line")
+    L, R = (1, int(problem["Z"])) if is_line else (int(problem["L"]), int(problem["R"]))
+    members = cport.num_threads() if is_line else 1
     # size the per-step sample so the whole run takes ~1-2 minutes
     t0 = time.perf_counter()
-    cport.sh_steps(problem, nsteps=1)
+    cpu_steps(problem, 1, members)
     t1 = max(time.perf_counter() - t0, 1e-6)
     total_budget = 90.0
     n_t = int(max(1, min(200, total_budget / ((args.steps + args.warmup) * t1))))
     for _ in range(args.warmup):
-        cport.sh_steps(problem, nsteps=n_t)
+        cpu_steps(problem, n_t, members)
     t0 = time.perf_counter()
+    upd = 0
     for _ in range(args.steps):
-        cport.sh_steps(problem, nsteps=n_t)
+        upd += cpu_steps(problem, n_t, members)
     dt = time.perf_counter() - t0
-    value = args.steps * n_t * L * R / dt
+    value = upd / dt
     cores = cport.num_threads()
-    sample = f"{n_t} of {len(problem['taus'])} time steps of the same mesh per bench step"
+    sample = f"{n_t} of {len(problem['taus'])} time steps of the same mesh per bench step ({members} member(s))"
     line = {
         "impl": "reference", "metric": "grid-point updates/s (SphericalHarmonicMesh CN+split)", "value": value, "unit": "updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -190,24 +219,29 @@ def main():
 
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
 
-    problem, desc = build_workload(args.workload)
-    L, R = int(problem["L"]), int(problem["R"])
+    wl = build_workload(args.workload)
+    problem, desc = wl[0], wl[1]
+    batch = wl[2] if len(wl) > 2 else 1
+    is_line = str(problem["kind"]).startswith("line")
+    L, R = (1, int(problem["Z"])) if is_line else (int(problem["L"]), int(problem["R"]))
     n_t = len(problem["taus"]) if args.time_steps is None else min(args.time_steps, len(problem["taus"]))
     taus = np.ascontiguousarray(problem["taus"][:n_t])
-    fields = np.ascontiguousarray(problem["fields"][:n_t])
-    updates_per_step = n_t * L * R  # per GPU (one sim per GPU)
+    fields = np.ascontiguousarray((wl[3] if len(wl) > 3 else problem["fields"])[:n_t])
+    updates_per_step = n_t * L * R * batch  # per GPU
 
-    sim = engine.DeviceSimulation.from_problem(problem, batch=1, device=local_rank)
+    sim = engine.DeviceSimulation.from_problem(problem, batch=batch, device=local_rank)
     stream = torch.cuda.Stream()  # a capturable (non-legacy) stream: the engine replays CUDA graphs on it
     torch.cuda.set_stream(stream)
     sim.set_stream(stream.cuda_stream)
     what = nat.OBS_NORM | nat.OBS_INNER_PRODUCTS
 
     # pinned host buffers for the end-to-end path
-    g0_pinned = torch.from_numpy(np.ascontiguousarray(problem["g0"]).view(np.float64).reshape(L, R, 2)).pin_memory()
-    g0_np = g0_pinned.numpy().view(np.complex128).reshape(1, L, R)
-    gout_pinned = torch.empty((L, R, 2), dtype=torch.float64).pin_memory()
-    gout_np = gout_pinned.numpy().view(np.complex128).reshape(1, L, R)
+    g0_full = np.ascontiguousarray(np.broadcast_to(np.asarray(problem["g0"], dtype=np.complex128).reshape(1, L, R), (batch, L, R)))
+    g0_pinned = torch.from_numpy(g0_full.view(np.float64).reshape(batch, L, R, 2)).pin_memory()
+    g0_np = g0_pinned.numpy().view(np.complex128).reshape(batch, L, R)
+    gout_pinned = torch.empty((batch, L, R, 2), dtype=torch.float64).pin_memory()
+    gout_np = gout_pinned.numpy().view(np.complex128).reshape(batch, L, R)
+    del g0_full
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def barrier():
@@ -294,7 +328,7 @@ def main():
             dom = max(prof, key=lambda k: prof[k][0])
             dom_ms, dom_n = prof[dom]
             total_ms = sum(v[0] for v in prof.values())
-            alg_bytes = BYTES_PER_UPDATE * L * R  # the dominant kernel streams the whole psi once per launch
+            alg_bytes = BYTES_PER_UPDATE * L * R * batch  # the dominant kernel streams the whole psi once per launch
             achieved = alg_bytes / (dom_ms / dom_n * 1e-3) / 1e9
             roofline = {
                 "bound": "hbm", "kernel": f"k_unit<{dom}>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
@@ -307,9 +341,9 @@ def main():
     value = world * args.steps * updates_per_step / (ms * 1e-3)
     value_e2e = world * args.steps * updates_per_step / (ms_e2e * 1e-3)
     peak, peak_src = measured_peak_gbs()
-    n_states = len(problem["state_l"])
-    h2d = L * R * 16 + n_t * 8
-    d2h = L * R * 16 + 8 * (1 + 2 * n_states)
+    n_states = len(problem["state_rows"])
+    h2d = batch * L * R * 16 + n_t * batch * 8
+    d2h = batch * L * R * 16 + batch * 8 * (1 + 2 * n_states)
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -325,7 +359,7 @@ def main():
             "metric": "grid-point updates/s (SphericalHarmonicMesh CN+split)", "value": value, "unit": "updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "complex128 (f64)", "data": "synthetic",
-            "config": {"workload": desc, "mesh_points": L * R, "time_steps_per_step": n_t, "sims_per_gpu": 1, "parallelism": f"ensemble x{world} (independent sims, no collective)",
+            "config": {"workload": desc, "mesh_points": L * R, "time_steps_per_step": n_t, "sims_per_gpu": batch, "parallelism": f"ensemble x{world} (independent sims, no collective)",
                        "l2": "flushed between timed iterations (256 MB write); psi (16 B/pt) + CN factors (16 B/pt) are L2-resident within an iteration by design"},
             "hbm_roofline_frac_step": value / world * BYTES_PER_UPDATE / (peak * 1e9), "us_per_time_step": 1e3 * ms / args.steps / n_t,
             "roofline": roofline, "cpu_baseline": cpu_baseline,

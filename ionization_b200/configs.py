@@ -91,3 +91,38 @@ def config4_fields(problem, n_fluence=64, n_phase=64, pulse_width=200 * u.asec):
         for p in ph:
             cols.append(C.field_series(str(problem["kind"]), sinc_pulse(pulse_width, f, p), problem["times"], problem["time_step"]))
     return np.ascontiguousarray(np.array(cols).T)
+
+
+def line_problem(*, z_bound, z_points, kind="line_len_cn", pulse=None, pulse_width=200 * u.asec, time_step=1 * u.asec, n_steps=1000, mask=True):
+    """LineMesh inputs (configs[1]): Gaussian well -10 eV / 5 a0 (dev/potentials/gaussian_well.py:19-21 of the reference),
+    electron mass, variational ground state, t in [-n_steps/2, n_steps/2] dt."""
+    z, dz = C.line_z_grid(z_bound, z_points)
+    q, m = u.electron_charge, u.electron_mass
+    well = P.GaussianPotential(potential_extrema=-10 * u.eV, width=5 * u.bohr_radius)
+    state = S.GaussianWellState.from_potential(well, m)
+    pulse = pulse if pulse is not None else sinc_pulse(pulse_width)
+    times = C.time_grid(-n_steps / 2 * time_step, n_steps / 2 * time_step, time_step)[: n_steps + 1]
+    h_diag, h_off = C.line_hamiltonian(z, dz, well(r=z), m)
+    w_z, v_pref = C.line_coupling(z, dz, q, m)
+    g0 = np.asarray(state(z), dtype=np.complex128)
+    g0 = g0 / np.sqrt(np.real(np.sum(np.conj(g0) * g0)) * dz)
+    return dict(
+        kind=kind, Z=z_points, z=z, delta_z=dz, h_diag=h_diag, h_off=h_off, w_z=w_z, v_pref=v_pref, g0=g0, times=times, taus=C.taus_from_times(times),
+        fields=C.field_series(kind, pulse, times, time_step), time_step=time_step,
+        mask=(P.RadialCosineMask(0.8 * z_bound, z_bound, 8)(r=z).astype(np.float64) if mask else np.ones(z_points)),
+        state_rows=g0[None, :].copy(), initial_state_index=0, test_charge=q, test_mass=m,
+    )
+
+
+def config2(**kw):
+    """configs[1]: LineMesh 1D Gaussian well, 2^16 points, Crank-Nicolson length gauge (batch of Sinc pulses: scan_fields)"""
+    return line_problem(z_bound=2000 * u.bohr_radius, z_points=2 ** 16, kind="line_len_cn", **kw)
+
+
+def scan_fields(problem, fluences_jcm2, phases, pulse_width=200 * u.asec):
+    """fluence x CEP scan (ionization_scans/scan_mesh.py:40-68): fields [n_steps, len(fluences) * len(phases)]"""
+    cols = []
+    for f in fluences_jcm2:
+        for p in phases:
+            cols.append(C.field_series(str(problem["kind"]), sinc_pulse(pulse_width, f * u.Jcm2, p), problem["times"], problem["time_step"]))
+    return np.ascontiguousarray(np.array(cols).T)

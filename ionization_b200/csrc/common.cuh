@@ -99,11 +99,12 @@ ION_DEVINL void affine_scan_warp(cplx &P, cplx &B, int lane)
 }
 
 // smP/smB: 32 entries each, private to this call site (no reuse hazard inside one kernel phase).
-// `short_range`: the caller guarantees (k_scan_bound, checked on the host when the LU factors are built) that the
-// product of the multipliers over any whole warp is below 1e-30 in magnitude, so the inflow of a warp is its
-// neighbour's aggregate plus one correction term; everything dropped is < 1e-60 relative to the largest entry.
+// `reach` > 0: the caller guarantees (k_scan_bound, checked on the host when the LU factors are built) that the
+// product of the multipliers over any `reach` whole warps is below 1e-30 in magnitude, so the inflow of a warp is a
+// Horner sum over its reach+1 nearest neighbours; everything dropped is < 1e-30 relative to the largest entry times a
+// further full-warp product.  reach == 0: full block-wide scan.
 template <bool FWD>
-ION_DEVINL cplx affine_scan_block_exclusive(cplx P, cplx B, cplx *smP, cplx *smB, int tid, int nthreads, bool short_range)
+ION_DEVINL cplx affine_scan_block_exclusive(cplx P, cplx B, cplx *smP, cplx *smB, int tid, int nthreads, int reach)
 {
     const int lane = tid & 31, warp = tid >> 5, nw = nthreads >> 5;
     affine_scan_warp<FWD>(P, B, lane);
@@ -114,11 +115,10 @@ ION_DEVINL cplx affine_scan_block_exclusive(cplx P, cplx B, cplx *smP, cplx *smB
             smB[warp] = B;
         }
         __syncthreads();
-        if (short_range) {
-            const int src = FWD ? warp - 1 : warp + 1, src2 = FWD ? warp - 2 : warp + 2;
-            if (src >= 0 && src < nw) {
-                win = smB[src];
-                if (src2 >= 0 && src2 < nw) win = c_fma(smP[src], smB[src2], win);
+        if (reach > 0) {
+            for (int j = reach + 1; j >= 1; --j) {
+                const int src = FWD ? warp - j : warp + j;
+                if (src >= 0 && src < nw) win = c_fma(smP[src], win, smB[src]);
             }
         } else {
             cplx wP = (lane < nw) ? smP[lane] : c_make(1.0, 0.0);

@@ -108,7 +108,7 @@ struct ion_sim {
     bool have_h = false, have_coupling = false;
     double factored_tau = 0.0;
     bool factored = false;
-    bool short_scan = false;
+    int short_scan = 0;  // reach of the cross-warp scan inflow in warps; 0 = full scan
     int64_t launch_count = 0;
 
     // CUDA graphs: chunks of up to GRAPH_CHUNK consecutive steps are captured once and replayed; the kernels of a
@@ -268,7 +268,7 @@ ion::UnitParams base_params(ion_sim *s)
     p.T_seg = s->T_seg;
     p.H = s->H;
     p.l_begin = s->l_begin;
-    p.short_scan = s->short_scan ? 1 : 0;
+    p.short_scan = s->short_scan;
     return p;
 }
 
@@ -413,22 +413,34 @@ int ensure_factor(ion_sim *s, double tau)
                 // warp 0 in the forward direction / the last warp backwards have no inflow; their bound is irrelevant but harmless
                 mx = std::max(mx, hb[(size_t)l * nw + w]);
             }
-        s->short_scan = (nw > 1) && (mx < std::log(1e-30));
+        // reach = number of whole warps over which the product of multipliers falls below 1e-30
+        int reach = 0;
+        if (nw > 1 && mx < 0.0) {
+            reach = (int)std::ceil(std::log(1e30) / (-mx));
+            if (reach > 2) reach = 0;  // slow decay: full block-wide scan
+        }
+        if (const char *env = std::getenv("ION_FULL_SCAN"))
+            if (env[0] == '1') reach = 0;
+        s->short_scan = reach;
         if (s->program == ION_LINE_LEN_CN) {
-            if (s->T / 32 > 1 && !s->short_scan)
+            if (nw > 1 && reach == 0)
                 return fail(ION_ENOTSUP,
                             "LineMesh Crank-Nicolson rebuilds its pivots per warp and needs the LU multipliers to decay below 1e-30 "
-                            "over 128 rows; this time step is too large for the mesh spacing");
+                            "over 256 rows; this time step is too large for the mesh spacing");
             if (int rc = dev_alloc(&s->th, (size_t)s->Rp)) return rc;
             ion::k_make_th<<<(s->Rp + 127) / 128, 128, 0, s->stream>>>(s->h_diag, tau, s->R, s->M, s->T, s->th);
             CUDA_TRY(cudaGetLastError());
         }
-        if (s->S > 1 && !s->short_scan)
-            return fail(ION_ENOTSUP,
-                        "r_points > 4096 needs the Crank-Nicolson LU multipliers to decay below 1e-30 over 128 rows; this time "
-                        "step is too large for the radial spacing (reduce time_step or increase delta_r)");
-        if (const char *env = std::getenv("ION_FULL_SCAN"))
-            if (env[0] == '1') s->short_scan = false;
+        if (s->S > 1) {
+            // r-segments: the halo must cover the reach (plus one warp of margin for the r-pair edge effects)
+            const int H = 64 * reach;
+            if (reach == 0 || s->T_seg + 2 * H > 512)
+                return fail(ION_ENOTSUP,
+                            "r_points > 4096 needs the Crank-Nicolson LU multipliers to decay below 1e-30 within the segment halo; this "
+                            "time step is too large for the radial spacing (reduce time_step or increase the spacing)");
+            s->H = H;
+            s->Tc = s->T_seg + 2 * H;
+        }
     }
     s->factored = true;
     s->factored_tau = tau;
@@ -800,8 +812,8 @@ int ion_sim_create_sharded(int program, int64_t L_total, int64_t l_begin, int64_
     int64_t T = (R + M - 1) / M;
     T = (T + 31) / 32 * 32;
     int S = 1, T_seg = (int)T, H = 0;
-    if (T > 1024) {  // r-segments with halos (kernels.cuh)
-        T_seg = 384;
+    if (T > 1024) {  // r-segments with halos (kernels.cuh); the halo width is fixed when the LU factors are built
+        T_seg = (program == ION_LINE_LEN_CN) ? 256 : 384;
         H = 64;
         S = (int)((T + T_seg - 1) / T_seg);
         T = (int64_t)S * T_seg;

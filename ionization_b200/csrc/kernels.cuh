@@ -49,7 +49,7 @@ struct UnitParams {
     int l_begin;             // global index of channel 0 of psi
     int parity;              // parity (in GLOBAL l) of the lower channel of a pair
     int flags;
-    int short_scan;          // cross-warp inflow of the CN scans is short-ranged (see common.cuh)
+    int short_scan;          // reach of the cross-warp inflow of the CN scans in warps (0: full scan; see common.cuh)
 };
 
 // unit -> (first local channel, is pair).  Pairs are (l, l+1) with global l % 2 == parity.
@@ -162,7 +162,7 @@ ION_DEVINL void cn_load(CnFactors<M> &f, const cplx *__restrict__ wch, const cpl
 
 template <int M>
 ION_DEVINL void cn_channel(cplx (&g)[M], const CnFactors<M> &f, const double (&toff)[M], double toff_prev, int t, int T,
-                           cplx *sm, bool short_scan)
+                           cplx *sm, int short_scan)
 {
     const cplx(&w)[M] = f.w;
     const cplx Pt = f.P, Qt = f.Q;
@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         cn_load<M>(fA, p.w + lw * chan, p.aggP + lw * T, p.aggQ + lw * T, t, T, ok);
         if (pair) cn_load<M>(fB, p.w + (lw + 1) * chan, p.aggP + (lw + 1) * T, p.aggQ + (lw + 1) * T, t, T, ok);
     }
-    const bool short_scan = p.short_scan != 0;
+    const int short_scan = p.short_scan;
 
     if (PROG == PROG_ROT_CN_ROT) {
         RotAngles<M> ang;
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
             D[k] = c_make(1.0 - th.y, fma(sa, wz[k], th.x));  // 1 + i (tau h + tau E w_z)
         }
         line_cn_factors<M>(fA, D, toff, toff_prev, tl, xs);
-        cn_channel<M>(A, fA, toff, toff_prev, tl, Tc, sm_scan, true);
+        cn_channel<M>(A, fA, toff, toff_prev, tl, Tc, sm_scan, short_scan > 0 ? short_scan : 1);
         if (p.flags & F_MASK) {
             double mk[M];
             load_vec<M>(mk, p.mask, T, t, ok);
