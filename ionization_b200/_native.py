@@ -12,7 +12,7 @@ import numpy as np
 from . import exceptions
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libionization_b200.so")
+LIB_PATH = os.environ.get("ION_LIB") or os.path.join(_HERE, "_lib", "libionization_b200.so")  # ION_LIB: A/B experiments
 
 # mirrors of the header's constants
 ION_SH_LEN_SO = 0
@@ -92,7 +92,12 @@ def load():
         )
     lib = ctypes.CDLL(LIB_PATH)
     for name, (restype, argtypes) in SIGNATURES.items():
-        fn = getattr(lib, name)
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            if os.environ.get("ION_LIB"):  # an older build loaded for an A/B experiment
+                continue
+            raise
         fn.restype = restype
         fn.argtypes = argtypes
     _lib = lib

@@ -115,7 +115,14 @@ ION_DEVINL cplx affine_scan_block_exclusive(cplx P, cplx B, cplx *smP, cplx *smB
             smB[warp] = B;
         }
         __syncthreads();
-        if (reach > 0) {
+        if (reach == 1) {  // the common case, kept branch-light
+            const int src = FWD ? warp - 1 : warp + 1, src2 = FWD ? warp - 2 : warp + 2;
+            if (src >= 0 && src < nw) {
+                win = smB[src];
+                if (src2 >= 0 && src2 < nw) win = c_fma(smP[src], smB[src2], win);
+            }
+        } else if (reach > 1) {
+#pragma unroll 1
             for (int j = reach + 1; j >= 1; --j) {
                 const int src = FWD ? warp - j : warp + j;
                 if (src >= 0 && src < nw) win = c_fma(smP[src], win, smB[src]);

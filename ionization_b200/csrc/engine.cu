@@ -212,14 +212,16 @@ int launch_unit_prog(ion_sim *s, const ion::UnitParams &p, dim3 grid)
 {
     const size_t smem = unit_smem_bytes(s);
     const dim3 block(PROG == ion::PROG_ROT ? s->T_seg : s->Tc);
-#define ION_LAUNCH(TMAX)                                                                                            \
+#define ION_LAUNCH(MM, TMAX, SEG)                                                                                   \
     do {                                                                                                            \
-        auto kern = ion::k_unit<4, PROG, TMAX>;                                                                     \
+        auto kern = ion::k_unit<MM, PROG, TMAX, SEG>;                                                               \
         kern<<<grid, block, smem, s->stream>>>(p);                                                                  \
     } while (0)
-    if (s->tmax == 256) ION_LAUNCH(256);
-    else if (s->tmax == 512) ION_LAUNCH(512);
-    else ION_LAUNCH(1024);
+    if (s->S > 1) ION_LAUNCH(4, 512, true);  // r-segments: T_seg + 2H <= 512 threads
+    else if (s->M == 8) ION_LAUNCH(8, 256, false);  // eight rows per thread, 256-thread CTAs (r_points <= 2048)
+    else if (s->tmax == 256) ION_LAUNCH(4, 256, false);
+    else if (s->tmax == 512) ION_LAUNCH(4, 512, false);
+    else ION_LAUNCH(4, 1024, false);
 #undef ION_LAUNCH
     CUDA_TRY(cudaGetLastError());
     return ION_OK;
@@ -228,7 +230,7 @@ int launch_unit_prog(ion_sim *s, const ion::UnitParams &p, dim3 grid)
 template <int PROG>
 int set_unit_smem_attr()
 {
-    CUDA_TRY(cudaFuncSetAttribute(ion::k_unit<4, PROG, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(ion::k_unit<4, PROG, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     return ION_OK;
 }
 // kernels launched with more than 48 KB of dynamic shared memory (T > 704) need the opt-in; done once at creation,
@@ -808,7 +810,11 @@ int ion_sim_create_sharded(int program, int64_t L_total, int64_t l_begin, int64_
     }
     if (ion_device_count() <= device || device < 0)
         return fail(ION_ENODEVICE, "no CUDA device " + std::to_string(device) + " (the engine has no CPU path)");
-    const int M = 4;
+    int M = 4;
+    if (const char *env = std::getenv("ION_M"))
+    {
+        if (env[0] == '8' && R <= 2048) M = 8;              // experiment: 256 threads x 8 rows
+    }
     int64_t T = (R + M - 1) / M;
     T = (T + 31) / 32 * 32;
     int S = 1, T_seg = (int)T, H = 0;

@@ -79,20 +79,20 @@ template <int M>
 ION_DEVINL void load_rows(cplx (&g)[M], const cplx *base, int T, int t, bool ok)
 {
 #pragma unroll
-    for (int k = 0; k < M; ++k) g[k] = ok ? ld_c(base + (size_t)k * T + t) : c_zero();
+    for (int k = 0; k < M; ++k) g[k] = ok ? ld_c(base + k * T + t) : c_zero();
 }
 template <int M>
 ION_DEVINL void store_rows(const cplx (&g)[M], cplx *base, int T, int t, bool ok)
 {
     if (!ok) return;
 #pragma unroll
-    for (int k = 0; k < M; ++k) st_c(base + (size_t)k * T + t, g[k]);
+    for (int k = 0; k < M; ++k) st_c(base + k * T + t, g[k]);
 }
 template <int M>
 ION_DEVINL void load_vec(double (&v)[M], const double *base, int T, int t, bool ok)
 {
 #pragma unroll
-    for (int k = 0; k < M; ++k) v[k] = ok ? base[(size_t)k * T + t] : 0.0;
+    for (int k = 0; k < M; ++k) v[k] = ok ? base[k * T + t] : 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -154,8 +154,8 @@ ION_DEVINL void cn_load(CnFactors<M> &f, const cplx *__restrict__ wch, const cpl
                         const cplx *__restrict__ aggQ, int t, int T, bool ok)
 {
 #pragma unroll
-    for (int k = 0; k < M; ++k) f.w[k] = ok ? ld_c(wch + (size_t)k * T + t) : c_make(1.0, 0.0);
-    f.wprev = (ok && t > 0) ? ld_c(wch + (size_t)(M - 1) * T + t - 1) : c_zero();
+    for (int k = 0; k < M; ++k) f.w[k] = ok ? ld_c(wch + k * T + t) : c_make(1.0, 0.0);
+    f.wprev = (ok && t > 0) ? ld_c(wch + (M - 1) * T + t - 1) : c_zero();
     f.P = ok ? ld_c(aggP + t) : c_zero();
     f.Q = ok ? ld_c(aggQ + t) : c_zero();
 }
@@ -420,8 +420,8 @@ ION_DEVINL void line_cn_factors(CnFactors<M> &f, const cplx (&D)[M], const doubl
 // Crank-Nicolson recurrences are simply started from zero at the edge of the halo.  That is exact to < 1e-30
 // because the LU multipliers decay geometrically -- the host verifies (k_scan_bound) that their product over any 32
 // threads is below 1e-30 before it allows S > 1.  Halo results are discarded; only interior threads store.
-template <int M, int PROG, int TMAX>
-__global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) && TMAX <= 512) ? (1024 / TMAX) : 1)
+template <int M, int PROG, int TMAX, bool SEG>
+__global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) && TMAX <= 512) ? (M <= 4 ? 1024 / TMAX : 2) : 1)
     k_unit(const UnitParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -430,10 +430,11 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
 
     const int tl = threadIdx.x, Tc = blockDim.x;         // index inside the CTA: scans and exchanges
     const int T = p.T;                                   // row stride of the layout
-    const int seg = blockIdx.x % p.S, unit = blockIdx.x / p.S;
-    const int t = seg * p.T_seg - p.H + tl;              // thread index inside the channel: addressing
-    const bool ok = (t >= 0) && (t < T);
-    const bool mine = ok && (tl >= p.H) && (tl < p.H + p.T_seg);
+    // SEG == false (one CTA per channel, the common case): all of this folds away at compile time
+    const int seg = SEG ? (int)(blockIdx.x % p.S) : 0, unit = SEG ? (int)(blockIdx.x / p.S) : (int)blockIdx.x;
+    const int t = SEG ? seg * p.T_seg - p.H + tl : tl;   // thread index inside the channel: addressing
+    const bool ok = SEG ? ((t >= 0) && (t < T)) : true;
+    const bool mine = SEG ? (ok && (tl >= p.H) && (tl < p.H + p.T_seg)) : true;
     const int b = blockIdx.y;
     int l0;
     bool pair = true;
@@ -568,7 +569,7 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         cplx D[M];
 #pragma unroll
         for (int k = 0; k < M; ++k) {
-            cplx th = ok ? ld_c(p.th + (size_t)k * T + t) : c_zero();
+            cplx th = ok ? ld_c(p.th + k * T + t) : c_zero();
             D[k] = c_make(1.0 - th.y, fma(sa, wz[k], th.x));  // 1 + i (tau h + tau E w_z)
         }
         line_cn_factors<M>(fA, D, toff, toff_prev, tl, xs);
