@@ -72,6 +72,15 @@ ION_DEVINL void sincos_near(const SinCosBase &b, double theta, double *sn, doubl
     }
 }
 
+// Programmatic dependent launch (PDL).  Every kernel of a time step depends on the wavefunction written by the
+// previous one, but its prologue -- coefficient / LU-factor loads and all the trigonometry -- does not.  Kernels are
+// launched with the programmatic-stream-serialization attribute: pdl_launch_dependents() at the top lets the next
+// kernel's CTAs start as soon as every CTA of this one has started (i.e. during its last, partially filled wave), and
+// pdl_wait() blocks until the previous grid has completed and flushed its stores; it is placed just before the first
+// load of psi.  Both are no-ops for a kernel launched without the attribute.
+ION_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+ION_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // 128-bit global accesses of one complex128
 ION_DEVINL cplx ld_c(const cplx *p) { return *p; }
 ION_DEVINL void st_c(cplx *p, cplx v) { *p = v; }

@@ -123,6 +123,7 @@ struct ion_sim {
     size_t obs_chunk_cap = 0;
     bool own_stream = false;
     bool use_graphs = true;
+    bool use_pdl = true;
     bool capturing = false;
 
     // profiling
@@ -212,10 +213,22 @@ int launch_unit_prog(ion_sim *s, const ion::UnitParams &p, dim3 grid)
 {
     const size_t smem = unit_smem_bytes(s);
     const dim3 block(PROG == ion::PROG_ROT ? s->T_seg : s->Tc);
+    // programmatic dependent launch: the kernel's psi-independent prologue overlaps the previous kernel's tail
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = s->use_pdl ? 1 : 0;
 #define ION_LAUNCH(MM, TMAX, SEG)                                                                                   \
     do {                                                                                                            \
         auto kern = ion::k_unit<MM, PROG, TMAX, SEG>;                                                               \
-        kern<<<grid, block, smem, s->stream>>>(p);                                                                  \
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));                                                                \
     } while (0)
     if (s->S > 1) ION_LAUNCH(4, 512, true);  // r-segments: T_seg + 2H <= 512 threads
     else if (s->M == 8) ION_LAUNCH(8, 256, false);  // eight rows per thread, 256-thread CTAs (r_points <= 2048)
@@ -850,6 +863,7 @@ int ion_sim_create_sharded(int program, int64_t L_total, int64_t l_begin, int64_
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess) s->own_stream = true;
     else s->stream = 0;
     if (const char *env = std::getenv("ION_NO_GRAPHS")) s->use_graphs = !(env[0] == '1');
+    if (const char *env = std::getenv("ION_NO_PDL")) s->use_pdl = !(env[0] == '1');
     int rc = prepare_kernels(s);
     if (rc == ION_OK) rc = dev_alloc(&s->psi, (size_t)batch * L * s->Rp);
     if (rc == ION_OK) {

@@ -450,22 +450,27 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
     const double sb = p.scal_b ? p.scal_b[b] : 0.0;
 
     cplx A[M], B[M];
+    pdl_launch_dependents();  // see common.cuh: everything up to pdl_wait() is independent of psi
 
     if (PROG == PROG_ROT) {
         if (!pair && !(p.flags & F_MASK)) return;
         if (!mine) return;  // point-wise in r: no halo needed (launched with H = 0)
+        RotAngles<M> ang;
+        double mk[M];
+        if (pair) {
+            double vec[M];
+            load_vec<M>(vec, p.vec, T, t, true);
+            ang = rot_angles<M>(vec, (sa + sb) * p.cl[p.l_begin + l0]);
+        }
+        if (p.flags & F_MASK) load_vec<M>(mk, p.mask, T, t, true);
+        pdl_wait();
         load_rows<M>(A, base, T, t, true);
         if (pair) {
             load_rows<M>(B, base + chan, T, t, true);
-            double vec[M];
-            load_vec<M>(vec, p.vec, T, t, true);
-            const RotAngles<M> ang = rot_angles<M>(vec, (sa + sb) * p.cl[p.l_begin + l0]);
             if (p.flags & F_REAL_ROT) rotate_pair<M, true>(A, B, ang);
             else rotate_pair<M, false>(A, B, ang);
         }
         if (p.flags & F_MASK) {
-            double mk[M];
-            load_vec<M>(mk, p.mask, T, t, true);
 #pragma unroll
             for (int k = 0; k < M; ++k) {
                 A[k] = c_scale(A[k], mk[k]);
@@ -479,12 +484,13 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
 
     if (PROG == PROG_H2) {
         if (!pair) return;
-        load_rows<M>(A, base, T, t, ok);
-        load_rows<M>(B, base + chan, T, t, ok);
         double zv[M];
         load_vec<M>(zv, p.zvec, T, t, ok);
         double sc = sa * p.cl2[p.l_begin + l0];
         const RPairAngles<M> ang = rpair_angles<M>(zv, ok ? p.zprev[t] : 0.0, sc);
+        pdl_wait();
+        load_rows<M>(A, base, T, t, ok);
+        load_rows<M>(B, base + chan, T, t, ok);
         h2_pair<M>(A, B, ang, (p.flags & F_H2_REVERSE) != 0, tl, Tc, xs);
         store_rows<M>(A, base, T, t, mine);
         store_rows<M>(B, base + chan, T, t, mine);
@@ -495,8 +501,6 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
     double toff[M];
     load_vec<M>(toff, p.toff, T, t, ok);
     const double toff_prev = ok ? p.toff_prev[t] : 0.0;
-    load_rows<M>(A, base, T, t, ok);
-    if (pair) load_rows<M>(B, base + chan, T, t, ok);
     CnFactors<M> fA, fB;
     if (PROG != PROG_LINE_CN) {
         const bool single_channel_prog = (PROG == PROG_LINE_SO_LEN || PROG == PROG_LINE_SO_VEL);
@@ -505,28 +509,34 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         if (pair) cn_load<M>(fB, p.w + (lw + 1) * chan, p.aggP + (lw + 1) * T, p.aggQ + (lw + 1) * T, t, T, ok);
     }
     const int short_scan = p.short_scan;
+    // trigonometry of the programs that rotate before the solve: also independent of psi
+    RotAngles<M> rang;
+    RPairAngles<M> pang;
+    if (PROG == PROG_ROT_CN_ROT && pair) {
+        double vec[M];
+        load_vec<M>(vec, p.vec, T, t, ok);
+        rang = rot_angles<M>(vec, sa * p.cl[p.l_begin + l0]);
+    }
+    if (PROG == PROG_H2_CN_H2 && pair) {
+        double zv[M];
+        load_vec<M>(zv, p.zvec, T, t, ok);
+        pang = rpair_angles<M>(zv, ok ? p.zprev[t] : 0.0, sa * p.cl2[p.l_begin + l0]);
+    }
+    pdl_wait();
+    load_rows<M>(A, base, T, t, ok);
+    if (pair) load_rows<M>(B, base + chan, T, t, ok);
 
     if (PROG == PROG_ROT_CN_ROT) {
-        RotAngles<M> ang;
-        if (pair) {
-            double vec[M];
-            load_vec<M>(vec, p.vec, T, t, ok);
-            ang = rot_angles<M>(vec, sa * p.cl[p.l_begin + l0]);  // reused after the CN
-            rotate_pair<M, false>(A, B, ang);
-        }
+        const RotAngles<M> &ang = rang;  // reused after the CN
+        if (pair) rotate_pair<M, false>(A, B, ang);
         cn_channel<M>(A, fA, toff, toff_prev, tl, Tc, sm_scan, short_scan);
         if (pair) {
             cn_channel<M>(B, fB, toff, toff_prev, tl, Tc, sm_scan + 128, short_scan);
             rotate_pair<M, false>(A, B, ang);
         }
     } else if (PROG == PROG_H2_CN_H2) {
-        RPairAngles<M> ang;
-        if (pair) {
-            double zv[M];
-            load_vec<M>(zv, p.zvec, T, t, ok);
-            ang = rpair_angles<M>(zv, ok ? p.zprev[t] : 0.0, sa * p.cl2[p.l_begin + l0]);  // reused after the CN
-            h2_pair<M>(A, B, ang, false, tl, Tc, xs);  // (oe, oo)
-        }
+        const RPairAngles<M> &ang = pang;  // reused after the CN
+        if (pair) h2_pair<M>(A, B, ang, false, tl, Tc, xs);  // (oe, oo)
         cn_channel<M>(A, fA, toff, toff_prev, tl, Tc, sm_scan, short_scan);
         if (pair) {
             cn_channel<M>(B, fB, toff, toff_prev, tl, Tc, sm_scan + 128, short_scan);
