@@ -23,6 +23,7 @@
 
 #include "../../include/ionization_b200.h"
 #include "kernels.cuh"
+#include "resident.cuh"
 
 namespace {
 
@@ -54,10 +55,12 @@ enum KernelKind : int {
     KK_SWEEP_FLAT,
     KK_MASK,
     KK_OBSERVE,
+    KK_RESIDENT,
     KK_COUNT
 };
 const char *const kKernelNames[KK_COUNT] = {"rot",        "rot_cn_rot", "h2",        "h2_cn_h2", "cn",     "line_so_len",
-                                            "line_so_vel", "line_cn",    "sweep_flat", "mask",    "observe"};
+                                            "line_so_vel", "line_cn",    "sweep_flat", "mask",    "observe",
+                                            "resident"};
 
 template <typename T>
 int dev_alloc(T **p, size_t n)
@@ -124,6 +127,14 @@ struct ion_sim {
     bool own_stream = false;
     bool use_graphs = true;
     bool use_pdl = true;
+    // on-chip resident kernel (resident.cuh): LL mailboxes between neighbouring CTAs, abort flag, exchange counter
+    bool use_resident = true;
+    int resident_state = 0;  // 0: not examined, 1: eligible, -1: not eligible
+    uint4 *halo = nullptr;
+    unsigned *abort_flag = nullptr;
+    unsigned ll_seq = 0;
+    int64_t resident_steps = 0;
+    bool resident_dirty = false;  // time steps advanced by the resident kernel (bench.py: algorithmic bytes per launch)
     bool capturing = false;
 
     // profiling
@@ -142,6 +153,8 @@ struct ion_sim {
         if (scal_phase) cudaFree(scal_phase);
         if (th) cudaFree(th);
         if (obs_chunk) cudaFree(obs_chunk);
+        if (halo) cudaFree(halo);
+        if (abort_flag) cudaFree(abort_flag);
         for (auto &g : graphs)
             if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
         for (auto e : ev) cudaEventDestroy(e);
@@ -537,6 +550,111 @@ int upload_scalars(ion_sim *s, int64_t n_steps, const double *taus, const double
     return ION_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// on-chip resident path (resident.cuh)
+// ---------------------------------------------------------------------------------------------
+size_t resident_smem_bytes(const ion_sim *s, bool vel)
+{
+    const size_t T = (size_t)s->T, TH = T / 2;
+    size_t n = (16 * T + 4 * T + 128) * sizeof(cplx) + (9 * TH + (TH & 1)) * sizeof(double);
+    if (vel) n += 4 * T * sizeof(cplx);
+    return n;
+}
+
+const void *resident_kernel(const ion_sim *s)
+{
+    return s->program == ION_SH_VEL_SO ? (const void *)ion::k_resident<1> : (const void *)ion::k_resident<0>;
+}
+
+// Decide once per handle whether the simulation fits on chip: split-operator SphericalHarmonic program, even l_bound,
+// unsharded, <= 2048 radial rows, and ceil(L/4) x batch CTAs all co-resident (cooperative launch).
+int resident_prepare(ion_sim *s)
+{
+    if (s->resident_state != 0) return ION_OK;
+    s->resident_state = -1;
+    if (!s->use_resident) return ION_OK;
+    if (s->program != ION_SH_LEN_SO && s->program != ION_SH_VEL_SO) return ION_OK;
+    if ((s->L_total % 2) != 0 || s->L_own != s->L_total || s->M != 4 || s->S != 1 || s->T > 512) return ION_OK;
+    const bool vel = s->program == ION_SH_VEL_SO;
+    int coop = 0, sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s->device));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    if (!coop) return ION_OK;
+    const size_t smem = resident_smem_bytes(s, vel);
+    const void *fn = resident_kernel(s);
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return ION_OK;
+    }
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, s->T, smem));
+    const int nblk = (s->L + 3) / 4;
+    if ((long long)nblk * s->batch > (long long)per_sm * sms) return ION_OK;
+    const size_t n_box = (size_t)s->batch * nblk * 2 * 2 * 8 * s->T;
+    if (int rc = dev_alloc(&s->halo, n_box)) return rc;
+    CUDA_TRY(cudaMemsetAsync(s->halo, 0, n_box * sizeof(uint4), s->stream));
+    if (int rc = dev_alloc(&s->abort_flag, 1)) return rc;
+    CUDA_TRY(cudaMemsetAsync(s->abort_flag, 0, sizeof(unsigned), s->stream));
+    s->ll_seq = 0;
+    s->resident_state = 1;
+    return ION_OK;
+}
+
+int launch_resident(ion_sim *s, const double *scal_dev, int64_t n_steps)
+{
+    const bool vel = s->program == ION_SH_VEL_SO;
+    const int nblk = (s->L + 3) / 4;
+    const unsigned per_step = vel ? 4u : 2u;
+    if ((uint64_t)s->ll_seq + (uint64_t)n_steps * per_step > 0xF0000000ull) {  // sequence numbers about to wrap: start over
+        const size_t n_box = (size_t)s->batch * nblk * 2 * 2 * 8 * s->T;
+        CUDA_TRY(cudaMemsetAsync(s->halo, 0, n_box * sizeof(uint4), s->stream));
+        s->ll_seq = 0;
+    }
+    ion::ResidentParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.psi = s->psi;
+    p.w = s->w;
+    p.toff = s->toff;
+    p.vec = s->vec;
+    p.zvec = s->zvec;
+    p.zprev = s->zprev;
+    p.mask = s->mask;
+    p.cl = s->cl;
+    p.cl2 = s->cl2;
+    p.scal = scal_dev;
+    p.halo = s->halo;
+    p.abort_flag = s->abort_flag;
+    p.n_steps = n_steps;
+    p.spin_limit = 4000000000ll;  // ~2 s of SM clock
+    p.L = s->L;
+    p.T = s->T;
+    p.batch = s->batch;
+    p.short_scan = s->short_scan;
+    p.seq_base = s->ll_seq;
+    if (const char *env = std::getenv("ION_RES_DBG")) p.dbg = std::atoi(env);
+    s->ll_seq += (unsigned)(n_steps * per_step);
+    void *args[] = {&p};
+    prof_begin(s, KK_RESIDENT);
+    CUDA_TRY(cudaLaunchCooperativeKernel(resident_kernel(s), dim3(nblk, s->batch), dim3(s->T), args, resident_smem_bytes(s, vel), s->stream));
+    prof_end(s);
+    s->launch_count++;
+    s->resident_steps += n_steps;
+    s->resident_dirty = true;
+    return ION_OK;
+}
+
+// after a synchronisation point: did an exchange of the resident kernel time out?
+int check_resident_abort(ion_sim *s)
+{
+    if (!s->resident_dirty || !s->abort_flag) return ION_OK;
+    unsigned flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, s->abort_flag, sizeof(flag), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->resident_dirty = false;
+    if (flag) return fail(ION_ECUDA, "resident kernel: a boundary-channel exchange between CTAs timed out; the wavefunction of this handle is invalid");
+    return ION_OK;
+}
+
 int launch_observe(ion_sim *s, uint32_t what, double *dev_out)
 {
     ion::ObserveParams p;
@@ -644,7 +762,22 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
     for (int64_t n = 1; n < n_steps; ++n)
         if (std::fabs(taus[n] - taus[0]) > 1e-9 * std::fabs(taus[0])) uniform_tau = false;
 
-    if (!(s->use_graphs && uniform_tau && !s->profiling && s->stream != 0 && n_steps >= 4)) {
+    if (int rc = resident_prepare(s)) return rc;
+    if (s->resident_state == 1 && uniform_tau) {
+        // on-chip resident kernel: one persistent launch per stretch between observations
+        if (int rc = ensure_factor(s, taus[0])) return rc;
+        int64_t n0 = 0, k_obs = 0;
+        for (int64_t n = 0; n < n_steps; ++n) {
+            const bool obs = observe_mask && observe_mask[n];
+            if (!obs && n + 1 < n_steps) continue;
+            if (int rc = launch_resident(s, s->scal + (size_t)n0 * s->batch, n + 1 - n0)) return rc;
+            n0 = n + 1;
+            if (obs) {
+                if (int rc = launch_observe(s, what, s->obs_out + (size_t)k_obs * rec)) return rc;
+                ++k_obs;
+            }
+        }
+    } else if (!(s->use_graphs && uniform_tau && !s->profiling && s->stream != 0 && n_steps >= 4)) {
         bool pre_done = false;
         int64_t k_obs = 0;
         for (int64_t n = 0; n < n_steps; ++n) {
@@ -730,6 +863,7 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
     if (n_obs) {
         CUDA_TRY(cudaMemcpyAsync(out, s->obs_out, (size_t)n_obs * rec * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if (int rc = check_resident_abort(s)) return rc;
     }
     return ION_OK;
 }
@@ -864,6 +998,7 @@ int ion_sim_create_sharded(int program, int64_t L_total, int64_t l_begin, int64_
     else s->stream = 0;
     if (const char *env = std::getenv("ION_NO_GRAPHS")) s->use_graphs = !(env[0] == '1');
     if (const char *env = std::getenv("ION_NO_PDL")) s->use_pdl = !(env[0] == '1');
+    if (const char *env = std::getenv("ION_NO_RESIDENT")) s->use_resident = !(env[0] == '1');
     int rc = prepare_kernels(s);
     if (rc == ION_OK) rc = dev_alloc(&s->psi, (size_t)batch * L * s->Rp);
     if (rc == ION_OK) {
@@ -1060,7 +1195,7 @@ int ion_sim_read_g(ion_sim_t *s, void *g)
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(g, s->io_stage, n * s->R * sizeof(cplx), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    return ION_OK;
+    return check_resident_abort(s);
 }
 
 int ion_sim_step(ion_sim_t *s, int64_t n_steps, const double *taus, const double *fields)
@@ -1092,7 +1227,7 @@ int ion_sim_observe(ion_sim_t *s, uint32_t what, double *out)
     const size_t rec = (size_t)ion_sim_observation_size(s, what) * s->batch;
     CUDA_TRY(cudaMemcpyAsync(out, s->obs_out, rec * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    return ION_OK;
+    return check_resident_abort(s);
 }
 
 int ion_sim_run(ion_sim_t *s, int64_t n_steps, const double *taus, const double *fields, const uint8_t *observe_mask,
@@ -1102,7 +1237,7 @@ int ion_sim_run(ion_sim_t *s, int64_t n_steps, const double *taus, const double 
     int rc = run_impl(s, n_steps, taus, fields, observe_mask, what, out);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    return ION_OK;
+    return check_resident_abort(s);
 }
 
 int ion_sim_synchronize(ion_sim_t *s)
@@ -1110,7 +1245,7 @@ int ion_sim_synchronize(ion_sim_t *s)
     if (!s) return fail(ION_EINVAL, "sim is NULL");
     CUDA_TRY(cudaSetDevice(s->device));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    return ION_OK;
+    return check_resident_abort(s);
 }
 
 int ion_sim_halo_buffer(ion_sim_t *s, int which, void **device_ptr, int64_t *n_bytes)
