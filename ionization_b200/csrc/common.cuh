@@ -41,34 +41,58 @@ ION_DEVINL cplx shfl_c(cplx v, int src)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Incremental sincos.  A thread needs cos/sin of several nearby angles theta_k = sc * vec[k] (consecutive radial
-// rows: the angle varies smoothly with r).  One full-range sincos is taken at a base angle; the others are
-// obtained by rotating the base by d = theta_k - theta_0 with a Taylor polynomial when |d| < 2^-6 (truncation
-// error < 2e-22 relative, i.e. below double rounding) and by a full sincos otherwise.  Always derived from the
-// base, never chained, so errors do not accumulate.
+// sincos for rotation angles.  Every l<->l+1 rotation and every r-pair brick needs cos/sin of its own angle
+// theta = (tau * field) * c_l * v_j, and in the velocity gauge the trigonometry is more than half of all FP64 work.
+// The angles are small almost everywhere (config 3: |theta| < 0.08 for every h2 brick, < 0.7 for h1 beyond the first
+// hundred radial rows), so the common case must not pay for a general argument reduction:
+//   |theta| <= pi/4   polynomials only (fdlibm's minimax kernels, < 1 ulp)                      ~16 FP64 instructions
+//   |theta| <  2^20   two-term Cody-Waite reduction with FMA (exact to ~1 ulp of the remainder)  ~26
+//   otherwise         CUDA's sincos (Payne-Hanek)
+// Coefficients live in constant memory so that they are FMA operands, not materialised immediates.
 // ---------------------------------------------------------------------------------------------
-struct SinCosBase {
-    double theta, c, s;
-};
-ION_DEVINL SinCosBase sincos_base(double theta)
+__constant__ double kSinCoef[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03,  -1.98412698298579493134e-04,
+                                   2.75573137070700676789e-06,  -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+__constant__ double kCosCoef[6] = {4.16666666666666019037e-02,  -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+                                   -2.75573143513906633035e-07, 2.08757232129817482790e-09,  -1.13596475577881948265e-11};
+
+// sin and cos of r, |r| <= pi/4
+ION_DEVINL void sincos_kernel(double r, double *sn, double *cs)
 {
-    SinCosBase b;
-    b.theta = theta;
-    sincos(theta, &b.s, &b.c);
-    return b;
+    const double z = r * r;
+    double ps = fma(kSinCoef[5], z, kSinCoef[4]);
+    double pc = fma(kCosCoef[5], z, kCosCoef[4]);
+    ps = fma(ps, z, kSinCoef[3]);
+    pc = fma(pc, z, kCosCoef[3]);
+    ps = fma(ps, z, kSinCoef[2]);
+    pc = fma(pc, z, kCosCoef[2]);
+    ps = fma(ps, z, kSinCoef[1]);
+    pc = fma(pc, z, kCosCoef[1]);
+    ps = fma(ps, z, kSinCoef[0]);
+    pc = fma(pc, z, kCosCoef[0]);
+    *sn = fma(r * z, ps, r);
+    *cs = fma(z * z, pc, fma(-0.5, z, 1.0));
 }
-ION_DEVINL void sincos_near(const SinCosBase &b, double theta, double *sn, double *cs)
+
+// the rare huge-angle path, out of line so that the many inlined call sites stay small
+__device__ __noinline__ void sincos_huge(double theta, double *sn, double *cs) { sincos(theta, sn, cs); }
+
+ION_DEVINL void fast_sincos(double theta, double *sn, double *cs)
 {
-    const double d = theta - b.theta;
-    if (fabs(d) < 0.015625) {
-        const double d2 = d * d;
-        // sin d = d (1 - d2/6 (1 - d2/20 (1 - d2/42)));  1 - cos d = d2/2 (1 - d2/12 (1 - d2/30 (1 - d2/56)))
-        const double sd = d * fma(-d2 * (1.0 / 6.0), fma(-d2 * (1.0 / 20.0), fma(-d2, 1.0 / 42.0, 1.0), 1.0), 1.0);
-        const double q = 0.5 * d2 * fma(-d2 * (1.0 / 12.0), fma(-d2 * (1.0 / 30.0), fma(-d2, 1.0 / 56.0, 1.0), 1.0), 1.0);
-        *cs = b.c - fma(b.c, q, b.s * sd);
-        *sn = b.s - fma(b.s, q, -b.c * sd);
+    const double a = fabs(theta);
+    if (a <= 0.78539816339744830962) {
+        sincos_kernel(theta, sn, cs);
+    } else if (a < 1048576.0) {
+        const double k = rint(theta * 0.63661977236758134308);            // theta * 2/pi
+        double r = fma(-k, 1.57079632679489655800e+00, theta);             // pi/2, high part
+        r = fma(-k, 6.12323399573676603587e-17, r);                        // pi/2, low part
+        double s, c;
+        sincos_kernel(r, &s, &c);
+        const int q = (int)k;                                             // |k| < 2^20
+        const double ss = (q & 1) ? c : s, cc = (q & 1) ? s : c;
+        *sn = (q & 2) ? -ss : ss;
+        *cs = ((q + 1) & 2) ? -cc : cc;
     } else {
-        sincos(theta, sn, cs);
+        sincos_huge(theta, sn, cs);
     }
 }
 

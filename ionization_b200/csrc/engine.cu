@@ -13,6 +13,7 @@
 // on the same pair) and are fused across the step boundary whenever no observation is requested in between.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -24,6 +25,7 @@
 #include "../../include/ionization_b200.h"
 #include "kernels.cuh"
 #include "resident.cuh"
+#include "slab.cuh"
 
 namespace {
 
@@ -56,11 +58,12 @@ enum KernelKind : int {
     KK_MASK,
     KK_OBSERVE,
     KK_RESIDENT,
+    KK_SLAB,
     KK_COUNT
 };
 const char *const kKernelNames[KK_COUNT] = {"rot",        "rot_cn_rot", "h2",        "h2_cn_h2", "cn",     "line_so_len",
                                             "line_so_vel", "line_cn",    "sweep_flat", "mask",    "observe",
-                                            "resident"};
+                                            "resident",    "slab"};
 
 template <typename T>
 int dev_alloc(T **p, size_t n)
@@ -90,6 +93,12 @@ struct ion_sim {
     cudaStream_t stream = 0;
 
     cplx *psi = nullptr, *io_stage = nullptr;
+    // second wavefunction buffer of the out-of-place inter-solve kernel (slab.cuh); psi always names the buffer that
+    // holds the current state, psi_home the one it must be in whenever control returns to the caller
+    cplx *psi2 = nullptr, *psi_home = nullptr;
+    bool use_slab = true;
+    int slab_state = 0;  // 0: not examined, 1: usable, -1: not usable
+    int slab_G = 0, slab_slabs = 0, slab_chunks = 0, slab_Qc = 0, slab_nQ = 0, slab_threads = 0;
     cplx *h_diag = nullptr;
     double *h_off = nullptr;
     std::vector<double> h_off_host;
@@ -128,7 +137,7 @@ struct ion_sim {
     bool use_graphs = true;
     bool use_pdl = true;
     // on-chip resident kernel (resident.cuh): LL mailboxes between neighbouring CTAs, abort flag, exchange counter
-    bool use_resident = true;
+    bool use_resident = false;  // opt-in (ION_RESIDENT=1): slower than the streaming path on B200 as measured
     int resident_state = 0;  // 0: not examined, 1: eligible, -1: not eligible
     uint4 *halo = nullptr;
     unsigned *abort_flag = nullptr;
@@ -149,6 +158,7 @@ struct ion_sim {
                         mask, rvec,     cl,     cl2,   cl_z, scal, state_rows, state_first, state_order, partial, ip_out, obs_out};
         for (void *p : ptrs)
             if (p) cudaFree(p);
+        if (psi2) cudaFree(psi2);
         if (scal_chunk) cudaFree(scal_chunk);
         if (scal_phase) cudaFree(scal_phase);
         if (th) cudaFree(th);
@@ -477,16 +487,109 @@ int ensure_factor(ion_sim *s, double tau)
 
 bool fast_l_path(const ion_sim *s) { return (s->L_total % 2) == 0; }
 
-// one step; `pre_done`: the leading even rotation of this step was already fused into the previous step's tail;
-// `fuse_next`: fold the leading even rotation of the next step into this step's tail.
-int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, bool pre_done, bool fuse_next)
+// ---------------------------------------------------------------------------------------------
+// velocity-gauge inter-solve kernel (slab.cuh): one out-of-place pass replaces the five pair-local passes between two
+// Crank-Nicolson solves.  Decided once per handle: split-operator velocity gauge, even l_bound, unsharded, M = 4, S = 1.
+// ---------------------------------------------------------------------------------------------
+int slab_prepare(ion_sim *s)
+{
+    if (s->slab_state != 0) return ION_OK;
+    s->slab_state = -1;
+    if (!s->use_slab || s->program != ION_SH_VEL_SO || !fast_l_path(s)) return ION_OK;
+    if (s->L_own != s->L_total || s->M != 4 || s->S != 1 || s->L < 2) return ION_OK;
+    int G = 8;
+    if (const char *env = std::getenv("ION_SLAB_G")) {
+        const int v = std::atoi(env);
+        if (v == 4 || v == 8 || v == 16 || v == 32) G = v;
+    }
+    const int nQ = (s->L + 3) / 4;
+    int chunks = 1, Qc = nQ, loaded = nQ;
+    for (;; ++chunks) {
+        Qc = (nQ + chunks - 1) / chunks;
+        loaded = Qc + (chunks == 1 ? 0 : (chunks == 2 ? 1 : 2));
+        if (G * loaded <= 512 || Qc == 1) break;
+    }
+    if (G * loaded > 512) return ION_OK;
+    chunks = (nQ + Qc - 1) / Qc;
+    const int W = 4 * G - 4;
+    s->slab_G = G;
+    s->slab_Qc = Qc;
+    s->slab_nQ = nQ;
+    s->slab_chunks = chunks;
+    s->slab_slabs = s->R / W + 1;
+    s->slab_threads = (G * loaded + 31) / 32 * 32;
+    const size_t n = (size_t)s->batch * s->L * s->Rp;
+    if (int rc = dev_alloc(&s->psi2, n)) return rc;
+    CUDA_TRY(cudaMemsetAsync(s->psi2, 0, n * sizeof(cplx), s->stream));  // the padding rows are never written
+    CUDA_TRY(cudaFuncSetAttribute(ion::k_slab<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 512 * (int)sizeof(cplx)));
+    s->psi_home = s->psi;
+    s->slab_state = 1;
+    return ION_OK;
+}
+
+int launch_slab(ion_sim *s, const double *sa, const double *sb)
+{
+    ion::SlabParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.psi_in = s->psi;
+    p.psi_out = s->psi2;
+    p.vec = s->vec;
+    p.zvec = s->zvec;
+    p.mask = s->mask;
+    p.cl = s->cl;
+    p.cl2 = s->cl2;
+    p.scal_a = sa;
+    p.scal_b = sb;
+    p.L = s->L;
+    p.T = s->T;
+    p.R = s->R;
+    p.G = s->slab_G;
+    p.n_slabs = s->slab_slabs;
+    p.Qc = s->slab_Qc;
+    p.nQ = s->slab_nQ;
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(s->slab_slabs * s->slab_chunks, s->batch);
+    cfg.blockDim = dim3(s->slab_threads);
+    cfg.dynamicSmemBytes = 8 * (size_t)s->slab_threads * sizeof(cplx);
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = s->use_pdl ? 1 : 0;
+    prof_begin(s, KK_SLAB);
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_slab<512>, p));
+    prof_end(s);
+    s->launch_count++;
+    std::swap(s->psi, s->psi2);
+    return ION_OK;
+}
+
+// bring the current state back into the buffer the rest of the API (and every captured graph) starts from
+int restore_home(ion_sim *s)
+{
+    if (!s->psi_home || s->psi == s->psi_home) return ION_OK;
+    CUDA_TRY(cudaMemcpyAsync(s->psi2, s->psi, (size_t)s->batch * s->L * s->Rp * sizeof(cplx), cudaMemcpyDeviceToDevice, s->stream));
+    std::swap(s->psi, s->psi2);
+    s->launch_count++;
+    return ION_OK;
+}
+
+// what a step's tail does of the next step's head when the two are fused (no observation in between)
+int fuse_level(const ion_sim *s) { return s->slab_state == 1 ? 2 : 1; }
+
+// one step; `pre`: how much of this step's head was already done by the previous step's tail (0: nothing, 1: the leading
+// even rotation, 2: velocity gauge with the inter-solve kernel -- everything up to the odd-pair Crank-Nicolson kernel);
+// `fuse_next`: fold the head of the next step into this step's tail (to fuse_level()).
+int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, int pre, bool fuse_next)
 {
     using namespace ion;
     int rc = ION_OK;
     switch (s->program) {
         case ION_SH_LEN_SO:
             if (fast_l_path(s)) {
-                if (!pre_done && (rc = launch_unit(s, PROG_ROT, 0, 0, sa, nullptr))) return rc;
+                if (pre < 1 && (rc = launch_unit(s, PROG_ROT, 0, 0, sa, nullptr))) return rc;
                 if ((rc = launch_unit(s, PROG_ROT_CN_ROT, 1, 0, sa, nullptr))) return rc;
                 return launch_unit(s, PROG_ROT, 0, F_MASK, sa, fuse_next ? sb_next : nullptr);
             }
@@ -499,14 +602,15 @@ int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, bool pre_d
         case ION_SH_VEL_SO: {
             const bool fast = fast_l_path(s);
             if (fast) {
-                if (!pre_done && (rc = launch_unit(s, PROG_ROT, 0, F_REAL_ROT, sa, nullptr))) return rc;
-                if ((rc = launch_unit(s, PROG_ROT, 1, F_REAL_ROT, sa, nullptr))) return rc;
+                if (pre < 1 && (rc = launch_unit(s, PROG_ROT, 0, F_REAL_ROT, sa, nullptr))) return rc;
+                if (pre < 2 && (rc = launch_unit(s, PROG_ROT, 1, F_REAL_ROT, sa, nullptr))) return rc;
             } else {
                 if ((rc = launch_sweep_flat(s, 0, F_REAL_ROT, sa))) return rc;
                 if ((rc = launch_sweep_flat(s, 1, F_REAL_ROT, sa))) return rc;
             }
-            if ((rc = launch_unit(s, PROG_H2, 0, 0, sa, nullptr))) return rc;              // ee, eo
+            if (pre < 2 && (rc = launch_unit(s, PROG_H2, 0, 0, sa, nullptr))) return rc;   // ee, eo
             if ((rc = launch_unit(s, PROG_H2_CN_H2, 1, 0, sa, nullptr))) return rc;        // oe, oo, CN, oo, oe
+            if (fast && fuse_next && s->slab_state == 1) return launch_slab(s, sa, sb_next);  // eo ee h1_o h1_e mask | h1_e h1_o ee eo
             if ((rc = launch_unit(s, PROG_H2, 0, F_H2_REVERSE, sa, nullptr))) return rc;   // eo, ee
             if (fast) {
                 if ((rc = launch_unit(s, PROG_ROT, 1, F_REAL_ROT, sa, nullptr))) return rc;
@@ -725,7 +829,7 @@ int enqueue_steps(ion_sim *s, int64_t len, const double *scal, const uint8_t *pa
         const bool ob = pattern && pattern[n];
         const bool fuse_next = can_fuse && !ob && (n + 1 < len ? true : fuse_last);
         const double *sa = scal + (size_t)n * s->batch;
-        if (int rc = enqueue_step(s, sa, sa + s->batch, pre_done, fuse_next)) return rc;
+        if (int rc = enqueue_step(s, sa, sa + s->batch, pre_done ? fuse_level(s) : 0, fuse_next)) return rc;
         pre_done = fuse_next;
         if (ob) {
             if (int rc = launch_observe(s, what, obs + (size_t)k_obs * rec)) return rc;
@@ -733,7 +837,7 @@ int enqueue_steps(ion_sim *s, int64_t len, const double *scal, const uint8_t *pa
         }
     }
     if (pre_done_out) *pre_done_out = pre_done;
-    return ION_OK;
+    return restore_home(s);  // a captured chunk must end where it started
 }
 
 int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fields, const uint8_t *observe_mask, uint32_t what,
@@ -763,6 +867,7 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
         if (std::fabs(taus[n] - taus[0]) > 1e-9 * std::fabs(taus[0])) uniform_tau = false;
 
     if (int rc = resident_prepare(s)) return rc;
+    if (int rc = slab_prepare(s)) return rc;
     if (s->resident_state == 1 && uniform_tau) {
         // on-chip resident kernel: one persistent launch per stretch between observations
         if (int rc = ensure_factor(s, taus[0])) return rc;
@@ -785,13 +890,14 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
             const bool obs = observe_mask && observe_mask[n];
             const bool fuse_next = can_fuse && (n + 1 < n_steps) && !obs;
             const double *sa = s->scal + (size_t)n * s->batch;
-            if (int rc = enqueue_step(s, sa, sa + s->batch, pre_done, fuse_next)) return rc;
+            if (int rc = enqueue_step(s, sa, sa + s->batch, pre_done ? fuse_level(s) : 0, fuse_next)) return rc;
             pre_done = fuse_next;
             if (obs) {
                 if (int rc = launch_observe(s, what, s->obs_out + (size_t)k_obs * rec)) return rc;
                 ++k_obs;
             }
         }
+        if (int rc = restore_home(s)) return rc;
     } else {
         if (int rc = ensure_factor(s, taus[0])) return rc;
         if (!s->scal_chunk)
@@ -998,7 +1104,9 @@ int ion_sim_create_sharded(int program, int64_t L_total, int64_t l_begin, int64_
     else s->stream = 0;
     if (const char *env = std::getenv("ION_NO_GRAPHS")) s->use_graphs = !(env[0] == '1');
     if (const char *env = std::getenv("ION_NO_PDL")) s->use_pdl = !(env[0] == '1');
-    if (const char *env = std::getenv("ION_NO_RESIDENT")) s->use_resident = !(env[0] == '1');
+    if (const char *env = std::getenv("ION_RESIDENT")) s->use_resident = (env[0] == '1');
+    if (const char *env = std::getenv("ION_NO_RESIDENT")) s->use_resident = s->use_resident && !(env[0] == '1');
+    if (const char *env = std::getenv("ION_NO_SLAB")) s->use_slab = !(env[0] == '1');
     int rc = prepare_kernels(s);
     if (rc == ION_OK) rc = dev_alloc(&s->psi, (size_t)batch * L * s->Rp);
     if (rc == ION_OK) {

@@ -108,11 +108,8 @@ template <int M>
 ION_DEVINL RotAngles<M> rot_angles(const double (&vec)[M], double sc)
 {
     RotAngles<M> a;
-    const SinCosBase base = sincos_base(sc * vec[0]);
-    a.c[0] = base.c;
-    a.s[0] = base.s;
 #pragma unroll
-    for (int k = 1; k < M; ++k) sincos_near(base, sc * vec[k], &a.s[k], &a.c[k]);
+    for (int k = 0; k < M; ++k) fast_sincos(sc * vec[k], &a.s[k], &a.c[k]);
     return a;
 }
 template <int M, bool REAL>
@@ -208,7 +205,7 @@ ION_DEVINL void cn_channel(cplx (&g)[M], const CnFactors<M> &f, const double (&t
 // ---------------------------------------------------------------------------------------------
 // cos/sin of the r-pair angles of one thread: pairs starting at even local rows k = 0, 2, .. (index k/2), at odd
 // local rows k = 1, 3, .., M-1 (index (k-1)/2; the last one is the pair shared with thread t+1) and the pair
-// (t*M-1, t*M) shared with thread t-1.  One full sincos, the rest incremental (common.cuh).
+// (t*M-1, t*M) shared with thread t-1.
 template <int M>
 struct RPairAngles {
     double ce[M / 2], se[M / 2], co[M / 2], so[M / 2], cp, sp;
@@ -217,14 +214,11 @@ template <int M>
 ION_DEVINL RPairAngles<M> rpair_angles(const double (&zv)[M], double zprev, double sc)
 {
     RPairAngles<M> a;
-    const SinCosBase base = sincos_base(sc * zv[0]);
-    a.ce[0] = base.c;
-    a.se[0] = base.s;
 #pragma unroll
-    for (int k = 2; k < M; k += 2) sincos_near(base, sc * zv[k], &a.se[k / 2], &a.ce[k / 2]);
+    for (int k = 0; k < M; k += 2) fast_sincos(sc * zv[k], &a.se[k / 2], &a.ce[k / 2]);
 #pragma unroll
-    for (int k = 1; k < M; k += 2) sincos_near(base, sc * zv[k], &a.so[k / 2], &a.co[k / 2]);
-    sincos_near(base, sc * zprev, &a.sp, &a.cp);
+    for (int k = 1; k < M; k += 2) fast_sincos(sc * zv[k], &a.so[k / 2], &a.co[k / 2]);
+    fast_sincos(sc * zprev, &a.sp, &a.cp);
     return a;
 }
 
@@ -555,12 +549,10 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         double vec[M];
         load_vec<M>(vec, p.vec, T, t, ok);
         cplx ph[M];
-        const SinCosBase pbase = sincos_base(sa * vec[0]);
 #pragma unroll
         for (int k = 0; k < M; ++k) {
             double sn, cs;
-            if (k == 0) sn = pbase.s, cs = pbase.c;
-            else sincos_near(pbase, sa * vec[k], &sn, &cs);
+            fast_sincos(sa * vec[k], &sn, &cs);
             ph[k] = c_make(cs, -sn);
             A[k] = c_mul(ph[k], A[k]);
         }

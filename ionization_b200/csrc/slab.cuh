@@ -1,0 +1,279 @@
+// ionization_b200 -- the velocity-gauge INTER-SOLVE kernel (sm_100a).
+//
+// Between the Crank-Nicolson solves of two consecutive velocity-gauge time steps the reference applies
+// (evolution_methods.py:89-123 with mesh_operators.py:1204-1408)
+//
+//      step n:    h2_eo h2_ee   h1_o   h1_e   mask          step n+1:   h1_e   h1_o   h2_ee h2_eo
+//
+// i.e. five operators that alternate between the even l-pairs (2p, 2p+1) and the odd l-pairs (2p+1, 2p+2).  A kernel
+// that owns l-pairs (kernels.cuh) needs one pass over psi per operator -- five passes, each bound by L2/HBM bandwidth.
+// None of the five couples radial rows except the h2 bricks, which couple a row with its direct neighbours only.  So
+// this kernel tiles the mesh the other way: a CTA owns a SLAB of 4G - 4 consecutive radial rows (plus two halo rows
+// on either side, recomputed redundantly) of a CHUNK of l-quads (plus one halo quad on either side), applies all five
+// operators with psi held in registers, and writes the result to a second buffer (out of place: the halo of one CTA
+// is the interior of another).  One pass instead of five.
+//
+//   thread (q, g): channels 4q .. 4q+3 ("quad"), rows a + 4g .. a + 4g + 3 with a = slab * (4G - 4) - 3  (a is odd)
+//      stage 1  h2 on the even l-pairs, r-sublayers in reverse order (odd, even)         scalar s_a = tau A_n
+//      stage 2  h1 rotation of the odd l-pairs                                            s_a
+//      stage 3  h1 rotation of the even l-pairs by s_a + s_b, radial mask
+//      stage 4  h1 rotation of the odd l-pairs                                            s_b = tau A_{n+1}
+//      stage 5  h2 on the even l-pairs, r-sublayers (even, odd)                           s_b
+//   Both even l-pairs of a quad and the odd pair (4q+1, 4q+2) are thread-local.  The odd pairs (4q-1, 4q) and
+//   (4q+3, 4q+4) straddle two threads: before stages 2 and 4 every thread publishes its channels 4q and 4q+3 in shared
+//   memory and each of the two threads evaluates its own half of the rotation.
+//   Because a is odd, the r-pairs (odd row, next row) of an h2 sublayer are thread-local and so is the middle pair of
+//   the even sublayer; the even-sublayer pairs that straddle two row groups are completed with warp shuffles (the G
+//   row groups of a quad are G consecutive lanes, G a power of two <= 32).
+//   Halo: the stage order (odd, even, .., even, odd) makes the light cone two rows wide on either side in r and one
+//   quad (four channels) wide on either side in l.
+#pragma once
+#include "kernels.cuh"
+
+namespace ion {
+
+struct SlabParams {
+    const cplx *psi_in;    // [batch][L][4][T]
+    cplx *psi_out;         // [batch][L][4][T]
+    const double *vec;     // [4][T]   h1 coupling y_j, 0 in the padding
+    const double *zvec;    // [4][T]   h2 r-pair coupling z_j of the pair (j, j+1), 0 for j >= R-1
+    const double *mask;    // [4][T] or nullptr
+    const double *cl;      // [L-1]    h1 l-pair coefficient
+    const double *cl2;     // [L-1]    h2 l-pair coefficient
+    const double *scal_a;  // [batch]  tau * A of the step whose tail this is
+    const double *scal_b;  // [batch]  tau * A of the next step
+    int L, T, R;
+    int G;                 // row groups per slab; 4G rows are loaded, the middle 4G - 4 are stored
+    int n_slabs;           // blockIdx.x % n_slabs
+    int Qc;                // interior quads per chunk; chunk = blockIdx.x / n_slabs
+    int nQ;                // quads in all: ceil(L / 4)
+};
+
+// position of row r (>= 0) in the row-interleaved layout with M = 4
+ION_DEVINL int slab_pos(int r, int T) { return (r & 3) * T + (r >> 2); }
+
+struct Trig {
+    double c, s;
+};
+ION_DEVINL Trig trig_of(double theta)
+{
+    Trig t;
+    fast_sincos(theta, &t.s, &t.c);
+    return t;
+}
+
+// r-pair brick on (lo, hi) of the Hadamard-transformed pair (S, D): S by +theta, D by -theta  (mesh_operators.py:1247-1408)
+ION_DEVINL void brick(cplx &Slo, cplx &Shi, cplx &Dlo, cplx &Dhi, const Trig &t)
+{
+    const cplx s0 = Slo, s1 = Shi, d0 = Dlo, d1 = Dhi;
+    Slo = c_make(fma(t.c, s0.x, t.s * s1.x), fma(t.c, s0.y, t.s * s1.y));
+    Shi = c_make(fma(t.c, s1.x, -t.s * s0.x), fma(t.c, s1.y, -t.s * s0.y));
+    Dlo = c_make(fma(t.c, d0.x, -t.s * d1.x), fma(t.c, d0.y, -t.s * d1.y));
+    Dhi = c_make(fma(t.c, d1.x, t.s * d0.x), fma(t.c, d1.y, t.s * d0.y));
+}
+// the lower / upper member only (the partner row lives in the neighbouring lane)
+ION_DEVINL void brick_lower(cplx &Slo, cplx &Dlo, const cplx Shi, const cplx Dhi, const Trig &t)
+{
+    Slo = c_make(fma(t.c, Slo.x, t.s * Shi.x), fma(t.c, Slo.y, t.s * Shi.y));
+    Dlo = c_make(fma(t.c, Dlo.x, -t.s * Dhi.x), fma(t.c, Dlo.y, -t.s * Dhi.y));
+}
+ION_DEVINL void brick_upper(cplx &Shi, cplx &Dhi, const cplx Slo, const cplx Dlo, const Trig &t)
+{
+    Shi = c_make(fma(t.c, Shi.x, -t.s * Slo.x), fma(t.c, Shi.y, -t.s * Slo.y));
+    Dhi = c_make(fma(t.c, Dhi.x, t.s * Dlo.x), fma(t.c, Dhi.y, t.s * Dlo.y));
+}
+
+// h2 on one l-pair (A = lower channel, B = upper) for the four rows of this thread.  ang[0]: pair (r0-1, r0) shared with
+// the previous row group; ang[1]: (r0, r1); ang[2]: (r1, r2); ang[3]: (r2, r3); ang[4]: (r3, r3+1) shared with the next group.
+// r0 is odd: ang[1], ang[3] belong to the odd sublayer, ang[0], ang[2], ang[4] to the even sublayer.
+template <bool REVERSE>
+ION_DEVINL void slab_h2(cplx (&A)[4], cplx (&B)[4], const Trig (&ang)[5], bool has_prev, bool has_next)
+{
+    hadamard<4>(A, B);  // A = S, B = D
+    if (REVERSE) {
+        brick(A[0], A[1], B[0], B[1], ang[1]);
+        brick(A[2], A[3], B[2], B[3], ang[3]);
+    }
+    {   // even sublayer: (r1, r2) local; (r3, next r0) and (prev r3, r0) with the neighbouring lanes
+        const cplx nS0 = shfl_down_c(A[0], 1), nD0 = shfl_down_c(B[0], 1);
+        const cplx pS3 = shfl_up_c(A[3], 1), pD3 = shfl_up_c(B[3], 1);
+        brick(A[1], A[2], B[1], B[2], ang[2]);
+        if (has_next) brick_lower(A[3], B[3], nS0, nD0, ang[4]);
+        if (has_prev) brick_upper(A[0], B[0], pS3, pD3, ang[0]);
+    }
+    if (!REVERSE) {
+        brick(A[0], A[1], B[0], B[1], ang[1]);
+        brick(A[2], A[3], B[2], B[3], ang[3]);
+    }
+    hadamard<4>(A, B);
+}
+
+ION_DEVINL void slab_h2_angles(Trig (&ang)[5], const double (&z)[5], double kappa)
+{
+#pragma unroll
+    for (int j = 0; j < 5; ++j) ang[j] = trig_of(kappa * z[j]);
+}
+
+ION_DEVINL void slab_rot_angles(Trig (&ang)[4], const double (&v)[4], double kappa)
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ang[j] = trig_of(kappa * v[j]);
+}
+// real rotation [[c, s], [-s, c]] of the l-pair (A lower, B upper)  mesh_operators.py:1204-1245
+ION_DEVINL void slab_rot(cplx (&A)[4], cplx (&B)[4], const Trig (&ang)[4])
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const cplx a = A[j], b = B[j];
+        A[j] = c_make(fma(ang[j].c, a.x, ang[j].s * b.x), fma(ang[j].c, a.y, ang[j].s * b.y));
+        B[j] = c_make(fma(ang[j].c, b.x, -ang[j].s * a.x), fma(ang[j].c, b.y, -ang[j].s * a.y));
+    }
+}
+ION_DEVINL void slab_rot_lower(cplx (&A)[4], const cplx (&B)[4], const Trig (&ang)[4])  // A = lower member, B read-only
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        A[j] = c_make(fma(ang[j].c, A[j].x, ang[j].s * B[j].x), fma(ang[j].c, A[j].y, ang[j].s * B[j].y));
+}
+ION_DEVINL void slab_rot_upper(const cplx (&A)[4], cplx (&B)[4], const Trig (&ang)[4])  // B = upper member, A read-only
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        B[j] = c_make(fma(ang[j].c, B[j].x, -ang[j].s * A[j].x), fma(ang[j].c, B[j].y, -ang[j].s * A[j].y));
+}
+
+// grid = (n_slabs * n_chunks, batch), block = NT (multiple of 32, NT >= G * (Qc + 2)); dynamic smem = 8 * NT cplx
+template <int NTMAX>
+__global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *xch = reinterpret_cast<cplx *>(smem_raw);  // [2 edges][4 rows][NT]
+
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int G = p.G, T = p.T, L = p.L;
+    const int g = tid & (G - 1), ql = tid / G;
+    const int slab = blockIdx.x % p.n_slabs, chunk = blockIdx.x / p.n_slabs;
+    const int b = blockIdx.y;
+    const int q_int0 = chunk * p.Qc, q_int1 = min(q_int0 + p.Qc, p.nQ);
+    const int q_first = q_int0 - (chunk > 0 ? 1 : 0);
+    const int q = q_first + ql;
+    const bool q_ok = q < min(q_int1 + 1, p.nQ);
+    const int l0 = 4 * q;
+    const int W = 4 * G - 4;
+    const int r0 = slab * W - 3 + 4 * g;  // first row of this thread (odd; may be negative or beyond R)
+
+    pdl_launch_dependents();
+
+    // ---- coefficients of this thread's rows (independent of psi) ----
+    double v[4], mk[4], z[5];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int r = r0 + j;
+        const bool ok = r >= 0 && r < p.R;
+        v[j] = ok ? p.vec[slab_pos(r, T)] : 0.0;
+        mk[j] = (ok && p.mask) ? p.mask[slab_pos(r, T)] : 1.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const int r = r0 - 1 + j;  // lower row of the pair
+        z[j] = (r >= 0 && r + 1 < p.R) ? p.zvec[slab_pos(r, T)] : 0.0;
+    }
+    const double sa = p.scal_a[b], sb = p.scal_b[b];
+    auto coef = [&](const double *c, int l) -> double { return (q_ok && l >= 0 && l + 1 < L) ? c[l] : 0.0; };
+    const bool has_prev = g > 0, has_next = g + 1 < G;
+
+    // ---- load psi: 4 channels x 4 rows ----
+    cplx X[4][4];
+    pdl_wait();
+    {
+        const cplx *base = p.psi_in + ((size_t)b * L + l0) * 4 * T;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = r0 + j;
+                const bool ok = q_ok && (l0 + c < L) && r >= 0 && r < p.R;
+                X[c][j] = ok ? ld_c(base + (size_t)c * 4 * T + slab_pos(r, T)) : c_zero();
+            }
+        }
+    }
+
+    // ---- stage 1: h2 (reversed) on (0,1), (2,3) with s_a ----
+    {
+        Trig ang[5];
+        slab_h2_angles(ang, z, sa * coef(p.cl2, l0));
+        slab_h2<true>(X[0], X[1], ang, has_prev, has_next);
+        slab_h2_angles(ang, z, sa * coef(p.cl2, l0 + 2));
+        slab_h2<true>(X[2], X[3], ang, has_prev, has_next);
+    }
+    // ---- stages 2 and 4: odd l-pairs; stage 3 in between ----
+    const int up = tid + G, dn = tid - G;  // threads holding the same rows of the next / previous quad
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const double s = pass == 0 ? sa : sb;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            xch[(0 * 4 + j) * NT + tid] = X[0][j];
+            xch[(1 * 4 + j) * NT + tid] = X[3][j];
+        }
+        __syncthreads();
+        {
+            Trig ang[4];
+            slab_rot_angles(ang, v, s * coef(p.cl, l0 + 1));
+            slab_rot(X[1], X[2], ang);
+        }
+        if (ql > 0) {  // pair (l0 - 1, l0): my channel 0 is the upper member
+            cplx nb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) nb[j] = xch[(1 * 4 + j) * NT + dn];
+            Trig ang[4];
+            slab_rot_angles(ang, v, s * coef(p.cl, l0 - 1));
+            slab_rot_upper(nb, X[0], ang);
+        }
+        if (up < NT) {  // pair (l0 + 3, l0 + 4): my channel 3 is the lower member
+            cplx nb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) nb[j] = xch[(0 * 4 + j) * NT + up];
+            Trig ang[4];
+            slab_rot_angles(ang, v, s * coef(p.cl, l0 + 3));
+            slab_rot_lower(X[3], nb, ang);
+        }
+        if (pass == 0) {
+            // ---- stage 3: even l-pairs by s_a + s_b, mask ----
+            Trig ang[4];
+            slab_rot_angles(ang, v, (sa + sb) * coef(p.cl, l0));
+            slab_rot(X[0], X[1], ang);
+            slab_rot_angles(ang, v, (sa + sb) * coef(p.cl, l0 + 2));
+            slab_rot(X[2], X[3], ang);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) X[c][j] = c_scale(X[c][j], mk[j]);
+            }
+            __syncthreads();  // everybody has read the stage-2 edges: the exchange buffer may be overwritten
+        }
+    }
+    // ---- stage 5: h2 (forward) on (0,1), (2,3) with s_b ----
+    {
+        Trig ang[5];
+        slab_h2_angles(ang, z, sb * coef(p.cl2, l0));
+        slab_h2<false>(X[0], X[1], ang, has_prev, has_next);
+        slab_h2_angles(ang, z, sb * coef(p.cl2, l0 + 2));
+        slab_h2<false>(X[2], X[3], ang, has_prev, has_next);
+    }
+
+    // ---- store the interior: rows with 2 <= 4g + j < 4G - 2 of the interior quads ----
+    if (q_ok && q >= q_int0 && q < q_int1) {
+        cplx *base = p.psi_out + ((size_t)b * L + l0) * 4 * T;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = 4 * g + j, r = r0 + j;
+                if (l0 + c < L && idx >= 2 && idx < 4 * G - 2 && r >= 0 && r < p.R) st_c(base + (size_t)c * 4 * T + slab_pos(r, T), X[c][j]);
+            }
+        }
+    }
+}
+
+}  // namespace ion

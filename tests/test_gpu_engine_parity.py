@@ -302,3 +302,53 @@ def test_short_range_and_full_scans_agree(name, monkeypatch):
             monkeypatch.delenv(k)
     assert rel_err(out["default"], out["full_scan"]) < 1e-13
     assert rel_err(out["default"], out["no_graphs"]) == 0.0
+
+
+@pytest.mark.parametrize("name,n", [("sh_vel_so_60x8", None), ("c1_sh_vel_so_500x50", 201), ("known_sh_vel_so_500x200", 130)])
+def test_velocity_inter_solve_kernel_matches_pair_local_kernels(name, n, monkeypatch):
+    """the out-of-place slab kernel (five operators between two Crank-Nicolson solves in one pass, slab.cuh) against
+    the pair-local kernels it replaces; odd step counts exercise the copy back into the home buffer, l_bound = 50 a
+    partial last quad, 500 x 200 several slabs and every kind of halo"""
+    eng = _engine()
+    p = load_golden(name)
+    n = len(p["taus"]) if n is None else n
+    out = {}
+    for mode in ("slab", "pair_local"):
+        if mode == "pair_local":
+            monkeypatch.setenv("ION_NO_SLAB", "1")
+        with eng.DeviceSimulation.from_problem(p) as sim:
+            sim.step(p["taus"][:n], p["fields"][:n])
+            out[mode] = sim.read_g()[0]
+            launches = sim.launch_count
+        if mode == "pair_local":
+            monkeypatch.delenv("ION_NO_SLAB")
+        out[mode + "_launches"] = launches
+    assert rel_err(out["slab"], out["pair_local"]) < 1e-13
+    assert out["slab_launches"] < out["pair_local_launches"]  # the slab path really ran
+
+
+def test_velocity_inter_solve_kernel_with_sparse_observations_and_ensemble():
+    """observation pattern with fused stretches of odd and even length in between, three ensemble members with
+    different pulses: run() with the slab kernel equals member-by-member runs without it"""
+    import os
+
+    eng = _engine()
+    p = load_golden("sh_vel_so_datastores_120x12")
+    n = len(p["taus"])
+    fields = np.stack([p["fields"], 0.5 * p["fields"], -1.3 * p["fields"]], axis=1)
+    pattern = np.zeros(n, dtype=np.uint8)
+    pattern[[2, 3, 9, 14, n - 1]] = 1
+    what = eng.nat.OBS_NORM | eng.nat.OBS_INNER_PRODUCTS
+    with eng.DeviceSimulation.from_problem(p, batch=3) as sim:
+        rec = sim.run(p["taus"], fields, pattern, what)
+        g = sim.read_g()
+    os.environ["ION_NO_SLAB"] = "1"
+    try:
+        for b in range(3):
+            with eng.DeviceSimulation.from_problem(p) as sim:
+                rec_b = sim.run(p["taus"], np.ascontiguousarray(fields[:, b]), pattern, what)
+                g_b = sim.read_g()[0]
+            assert rel_err(g[b], g_b) < 1e-13
+            assert np.max(np.abs(rec[:, b, :] - rec_b[:, 0, :])) < 1e-13
+    finally:
+        del os.environ["ION_NO_SLAB"]
