@@ -73,26 +73,50 @@ ION_DEVINL void sincos_kernel(double r, double *sn, double *cs)
     *cs = fma(z * z, pc, fma(-0.5, z, 1.0));
 }
 
-// the rare huge-angle path, out of line so that the many inlined call sites stay small
-__device__ __noinline__ void sincos_huge(double theta, double *sn, double *cs) { sincos(theta, sn, cs); }
-
-ION_DEVINL void fast_sincos(double theta, double *sn, double *cs)
+// the rare huge-angle path, out of line (and by value: no pointer escapes that would force the results into local memory)
+__device__ __noinline__ double2 sincos_huge(double theta)
 {
-    const double a = fabs(theta);
-    if (a <= 0.78539816339744830962) {
-        sincos_kernel(theta, sn, cs);
-    } else if (a < 1048576.0) {
-        const double k = rint(theta * 0.63661977236758134308);            // theta * 2/pi
-        double r = fma(-k, 1.57079632679489655800e+00, theta);             // pi/2, high part
-        r = fma(-k, 6.12323399573676603587e-17, r);                        // pi/2, low part
-        double s, c;
-        sincos_kernel(r, &s, &c);
-        const int q = (int)k;                                             // |k| < 2^20
-        const double ss = (q & 1) ? c : s, cc = (q & 1) ? s : c;
-        *sn = (q & 2) ? -ss : ss;
-        *cs = ((q + 1) & 2) ? -cc : cc;
+    double2 r;
+    sincos(theta, &r.x, &r.y);
+    return r;
+}
+
+// reduction + kernels, |theta| < 2^20
+ION_DEVINL void sincos_reduced(double theta, double *sn, double *cs)
+{
+    const double k = rint(theta * 0.63661977236758134308);  // theta * 2/pi
+    double r = fma(-k, 1.57079632679489655800e+00, theta);   // pi/2, high part
+    r = fma(-k, 6.12323399573676603587e-17, r);              // pi/2, low part
+    double s, c;
+    sincos_kernel(r, &s, &c);
+    const int q = (int)k;
+    const double ss = (q & 1) ? c : s, cc = (q & 1) ? s : c;
+    *sn = (q & 2) ? -ss : ss;
+    *cs = ((q + 1) & 2) ? -cc : cc;
+}
+
+// cos/sin of N angles of one thread.  The path is chosen per WARP (a vote over the converged lanes), so the N
+// evaluations of a path are straight-line code the scheduler can interleave, and warps never diverge here.
+template <int N>
+ION_DEVINL void fast_sincos_n(const double (&theta)[N], double (&sn)[N], double (&cs)[N])
+{
+    double amax = fabs(theta[0]);
+#pragma unroll
+    for (int k = 1; k < N; ++k) amax = fmax(amax, fabs(theta[k]));
+    const unsigned lanes = __activemask();
+    if (__all_sync(lanes, amax <= 0.78539816339744830962)) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) sincos_kernel(theta[k], &sn[k], &cs[k]);
+    } else if (__all_sync(lanes, amax < 1048576.0)) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) sincos_reduced(theta[k], &sn[k], &cs[k]);
     } else {
-        sincos_huge(theta, sn, cs);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {  // unrolled: a dynamic index would push the arrays into local memory
+            const double2 r = sincos_huge(theta[k]);
+            sn[k] = r.x;
+            cs[k] = r.y;
+        }
     }
 }
 

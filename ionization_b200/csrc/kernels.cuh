@@ -108,8 +108,10 @@ template <int M>
 ION_DEVINL RotAngles<M> rot_angles(const double (&vec)[M], double sc)
 {
     RotAngles<M> a;
+    double th[M];
 #pragma unroll
-    for (int k = 0; k < M; ++k) fast_sincos(sc * vec[k], &a.s[k], &a.c[k]);
+    for (int k = 0; k < M; ++k) th[k] = sc * vec[k];
+    fast_sincos_n<M>(th, a.s, a.c);
     return a;
 }
 template <int M, bool REAL>
@@ -214,11 +216,17 @@ template <int M>
 ION_DEVINL RPairAngles<M> rpair_angles(const double (&zv)[M], double zprev, double sc)
 {
     RPairAngles<M> a;
+    double th[M + 1], sn[M + 1], cs[M + 1];
 #pragma unroll
-    for (int k = 0; k < M; k += 2) fast_sincos(sc * zv[k], &a.se[k / 2], &a.ce[k / 2]);
+    for (int k = 0; k < M; ++k) th[k] = sc * zv[k];
+    th[M] = sc * zprev;
+    fast_sincos_n<M + 1>(th, sn, cs);
 #pragma unroll
-    for (int k = 1; k < M; k += 2) fast_sincos(sc * zv[k], &a.so[k / 2], &a.co[k / 2]);
-    fast_sincos(sc * zprev, &a.sp, &a.cp);
+    for (int k = 0; k < M; k += 2) a.se[k / 2] = sn[k], a.ce[k / 2] = cs[k];
+#pragma unroll
+    for (int k = 1; k < M; k += 2) a.so[k / 2] = sn[k], a.co[k / 2] = cs[k];
+    a.sp = sn[M];
+    a.cp = cs[M];
     return a;
 }
 
@@ -549,12 +557,16 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         double vec[M];
         load_vec<M>(vec, p.vec, T, t, ok);
         cplx ph[M];
+        {
+            double th[M], sn[M], cs[M];
 #pragma unroll
-        for (int k = 0; k < M; ++k) {
-            double sn, cs;
-            fast_sincos(sa * vec[k], &sn, &cs);
-            ph[k] = c_make(cs, -sn);
-            A[k] = c_mul(ph[k], A[k]);
+            for (int k = 0; k < M; ++k) th[k] = sa * vec[k];
+            fast_sincos_n<M>(th, sn, cs);
+#pragma unroll
+            for (int k = 0; k < M; ++k) {
+                ph[k] = c_make(cs[k], -sn[k]);
+                A[k] = c_mul(ph[k], A[k]);
+            }
         }
         cn_channel<M>(A, fA, toff, toff_prev, tl, Tc, sm_scan, short_scan);
 #pragma unroll

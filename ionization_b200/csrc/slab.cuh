@@ -55,12 +55,6 @@ ION_DEVINL int slab_pos(int r, int T) { return (r & 3) * T + (r >> 2); }
 struct Trig {
     double c, s;
 };
-ION_DEVINL Trig trig_of(double theta)
-{
-    Trig t;
-    fast_sincos(theta, &t.s, &t.c);
-    return t;
-}
 
 // r-pair brick on (lo, hi) of the Hadamard-transformed pair (S, D): S by +theta, D by -theta  (mesh_operators.py:1247-1408)
 ION_DEVINL void brick(cplx &Slo, cplx &Shi, cplx &Dlo, cplx &Dhi, const Trig &t)
@@ -108,16 +102,15 @@ ION_DEVINL void slab_h2(cplx (&A)[4], cplx (&B)[4], const Trig (&ang)[5], bool h
     hadamard<4>(A, B);
 }
 
-ION_DEVINL void slab_h2_angles(Trig (&ang)[5], const double (&z)[5], double kappa)
+template <int N>
+ION_DEVINL void slab_angles(Trig (&ang)[N], const double (&v)[N], double kappa)
 {
+    double th[N], sn[N], cs[N];
 #pragma unroll
-    for (int j = 0; j < 5; ++j) ang[j] = trig_of(kappa * z[j]);
-}
-
-ION_DEVINL void slab_rot_angles(Trig (&ang)[4], const double (&v)[4], double kappa)
-{
+    for (int j = 0; j < N; ++j) th[j] = kappa * v[j];
+    fast_sincos_n<N>(th, sn, cs);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) ang[j] = trig_of(kappa * v[j]);
+    for (int j = 0; j < N; ++j) ang[j].c = cs[j], ang[j].s = sn[j];
 }
 // real rotation [[c, s], [-s, c]] of the l-pair (A lower, B upper)  mesh_operators.py:1204-1245
 ION_DEVINL void slab_rot(cplx (&A)[4], cplx (&B)[4], const Trig (&ang)[4])
@@ -201,9 +194,9 @@ __global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
     // ---- stage 1: h2 (reversed) on (0,1), (2,3) with s_a ----
     {
         Trig ang[5];
-        slab_h2_angles(ang, z, sa * coef(p.cl2, l0));
+        slab_angles<5>(ang, z, sa * coef(p.cl2, l0));
         slab_h2<true>(X[0], X[1], ang, has_prev, has_next);
-        slab_h2_angles(ang, z, sa * coef(p.cl2, l0 + 2));
+        slab_angles<5>(ang, z, sa * coef(p.cl2, l0 + 2));
         slab_h2<true>(X[2], X[3], ang, has_prev, has_next);
     }
     // ---- stages 2 and 4: odd l-pairs; stage 3 in between ----
@@ -219,7 +212,7 @@ __global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
         __syncthreads();
         {
             Trig ang[4];
-            slab_rot_angles(ang, v, s * coef(p.cl, l0 + 1));
+            slab_angles<4>(ang, v, s * coef(p.cl, l0 + 1));
             slab_rot(X[1], X[2], ang);
         }
         if (ql > 0) {  // pair (l0 - 1, l0): my channel 0 is the upper member
@@ -227,7 +220,7 @@ __global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
 #pragma unroll
             for (int j = 0; j < 4; ++j) nb[j] = xch[(1 * 4 + j) * NT + dn];
             Trig ang[4];
-            slab_rot_angles(ang, v, s * coef(p.cl, l0 - 1));
+            slab_angles<4>(ang, v, s * coef(p.cl, l0 - 1));
             slab_rot_upper(nb, X[0], ang);
         }
         if (up < NT) {  // pair (l0 + 3, l0 + 4): my channel 3 is the lower member
@@ -235,15 +228,15 @@ __global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
 #pragma unroll
             for (int j = 0; j < 4; ++j) nb[j] = xch[(0 * 4 + j) * NT + up];
             Trig ang[4];
-            slab_rot_angles(ang, v, s * coef(p.cl, l0 + 3));
+            slab_angles<4>(ang, v, s * coef(p.cl, l0 + 3));
             slab_rot_lower(X[3], nb, ang);
         }
         if (pass == 0) {
             // ---- stage 3: even l-pairs by s_a + s_b, mask ----
             Trig ang[4];
-            slab_rot_angles(ang, v, (sa + sb) * coef(p.cl, l0));
+            slab_angles<4>(ang, v, (sa + sb) * coef(p.cl, l0));
             slab_rot(X[0], X[1], ang);
-            slab_rot_angles(ang, v, (sa + sb) * coef(p.cl, l0 + 2));
+            slab_angles<4>(ang, v, (sa + sb) * coef(p.cl, l0 + 2));
             slab_rot(X[2], X[3], ang);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -256,9 +249,9 @@ __global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
     // ---- stage 5: h2 (forward) on (0,1), (2,3) with s_b ----
     {
         Trig ang[5];
-        slab_h2_angles(ang, z, sb * coef(p.cl2, l0));
+        slab_angles<5>(ang, z, sb * coef(p.cl2, l0));
         slab_h2<false>(X[0], X[1], ang, has_prev, has_next);
-        slab_h2_angles(ang, z, sb * coef(p.cl2, l0 + 2));
+        slab_angles<5>(ang, z, sb * coef(p.cl2, l0 + 2));
         slab_h2<false>(X[2], X[3], ang, has_prev, has_next);
     }
 
