@@ -45,7 +45,8 @@ ION_DEVINL cplx shfl_c(cplx v, int src)
 // theta = (tau * field) * c_l * v_j, and in the velocity gauge the trigonometry is more than half of all FP64 work.
 // The angles are small almost everywhere (config 3: |theta| < 0.08 for every h2 brick, < 0.7 for h1 beyond the first
 // hundred radial rows), so the common case must not pay for a general argument reduction:
-//   |theta| <= pi/4   polynomials only (fdlibm's minimax kernels, < 1 ulp)                      ~16 FP64 instructions
+//   |theta| <= 2^-4   short Taylor polynomials                                                   ~11 FP64 instructions
+//   |theta| <= pi/4   polynomials only (fdlibm's minimax kernels, < 1 ulp)                      ~16
 //   |theta| <  2^20   two-term Cody-Waite reduction with FMA (exact to ~1 ulp of the remainder)  ~26
 //   otherwise         CUDA's sincos (Payne-Hanek)
 // Coefficients live in constant memory so that they are FMA operands, not materialised immediates.
@@ -54,6 +55,19 @@ __constant__ double kSinCoef[6] = {-1.66666666666666324348e-01, 8.33333333332248
                                    2.75573137070700676789e-06,  -2.50507602534068634195e-08, 1.58969099521155010221e-10};
 __constant__ double kCosCoef[6] = {4.16666666666666019037e-02,  -1.38888888888741095749e-03, 2.48015872894767294178e-05,
                                    -2.75573143513906633035e-07, 2.08757232129817482790e-09,  -1.13596475577881948265e-11};
+
+// sin and cos of r, |r| <= 2^-4: Taylor, truncation error < 3e-19 relative
+ION_DEVINL void sincos_tiny(double r, double *sn, double *cs)
+{
+    const double z = r * r;
+    double ps = fma(2.75573192239858906526e-06, z, -1.98412698412698412698e-04);  // 1/9!, -1/7!
+    double pc = fma(2.48015873015873015873e-05, z, -1.38888888888888888889e-03);  // 1/8!, -1/6!
+    ps = fma(ps, z, 8.33333333333333333333e-03);                                  // 1/5!
+    pc = fma(pc, z, 4.16666666666666666667e-02);                                  // 1/4!
+    ps = fma(ps, z, -1.66666666666666666667e-01);                                 // -1/3!
+    *sn = fma(r * z, ps, r);
+    *cs = fma(z * z, pc, fma(-0.5, z, 1.0));
+}
 
 // sin and cos of r, |r| <= pi/4
 ION_DEVINL void sincos_kernel(double r, double *sn, double *cs)
@@ -104,7 +118,10 @@ ION_DEVINL void fast_sincos_n(const double (&theta)[N], double (&sn)[N], double 
 #pragma unroll
     for (int k = 1; k < N; ++k) amax = fmax(amax, fabs(theta[k]));
     const unsigned lanes = __activemask();
-    if (__all_sync(lanes, amax <= 0.78539816339744830962)) {
+    if (__all_sync(lanes, amax <= 0.0625)) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) sincos_tiny(theta[k], &sn[k], &cs[k]);
+    } else if (__all_sync(lanes, amax <= 0.78539816339744830962)) {
 #pragma unroll
         for (int k = 0; k < N; ++k) sincos_kernel(theta[k], &sn[k], &cs[k]);
     } else if (__all_sync(lanes, amax < 1048576.0)) {

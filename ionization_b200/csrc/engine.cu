@@ -521,7 +521,7 @@ int slab_prepare(ion_sim *s)
     const size_t n = (size_t)s->batch * s->L * s->Rp;
     if (int rc = dev_alloc(&s->psi2, n)) return rc;
     CUDA_TRY(cudaMemsetAsync(s->psi2, 0, n * sizeof(cplx), s->stream));  // the padding rows are never written
-    CUDA_TRY(cudaFuncSetAttribute(ion::k_slab<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 512 * (int)sizeof(cplx)));
+    CUDA_TRY(cudaFuncSetAttribute(ion::k_slab<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 512 * (int)sizeof(cplx)));
     s->psi_home = s->psi;
     s->slab_state = 1;
     return ION_OK;
@@ -551,7 +551,7 @@ int launch_slab(ion_sim *s, const double *sa, const double *sb)
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(s->slab_slabs * s->slab_chunks, s->batch);
     cfg.blockDim = dim3(s->slab_threads);
-    cfg.dynamicSmemBytes = 8 * (size_t)s->slab_threads * sizeof(cplx);
+    cfg.dynamicSmemBytes = 12 * (size_t)s->slab_threads * sizeof(cplx);
     cfg.stream = s->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -83,7 +83,13 @@ ION_DEVINL void brick_upper(cplx &Shi, cplx &Dhi, const cplx Slo, const cplx Dlo
 template <bool REVERSE>
 ION_DEVINL void slab_h2(cplx (&A)[4], cplx (&B)[4], const Trig (&ang)[5], bool has_prev, bool has_next)
 {
-    hadamard<4>(A, B);  // A = S, B = D
+    // Hadamard over the l-pair without its 1/sqrt(2): the bricks are linear, both factors are applied at the end (1/2)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const cplx a = A[j], b = B[j];
+        A[j] = c_add(a, b);  // sqrt(2) S
+        B[j] = c_sub(a, b);  // sqrt(2) D
+    }
     if (REVERSE) {
         brick(A[0], A[1], B[0], B[1], ang[1]);
         brick(A[2], A[3], B[2], B[3], ang[3]);
@@ -99,7 +105,26 @@ ION_DEVINL void slab_h2(cplx (&A)[4], cplx (&B)[4], const Trig (&ang)[5], bool h
         brick(A[0], A[1], B[0], B[1], ang[1]);
         brick(A[2], A[3], B[2], B[3], ang[3]);
     }
-    hadamard<4>(A, B);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const cplx sv = A[j], d = B[j];
+        A[j] = c_make(0.5 * (sv.x + d.x), 0.5 * (sv.y + d.y));
+        B[j] = c_make(0.5 * (sv.x - d.x), 0.5 * (sv.y - d.y));
+    }
+}
+
+// the five r-pair angles of one l-pair: four evaluations, the pair shared with the previous row group comes from the
+// neighbouring lane (its ang[4])
+ION_DEVINL void slab_h2_angles(Trig (&ang)[5], const double (&z)[5], double kappa)
+{
+    double th[4], sn[4], cs[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) th[j] = kappa * z[j + 1];
+    fast_sincos_n<4>(th, sn, cs);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ang[j + 1].c = cs[j], ang[j + 1].s = sn[j];
+    ang[0].c = __shfl_up_sync(0xffffffffu, cs[3], 1);
+    ang[0].s = __shfl_up_sync(0xffffffffu, sn[3], 1);
 }
 
 template <int N>
@@ -135,12 +160,12 @@ ION_DEVINL void slab_rot_upper(const cplx (&A)[4], cplx (&B)[4], const Trig (&an
         B[j] = c_make(fma(ang[j].c, B[j].x, -ang[j].s * A[j].x), fma(ang[j].c, B[j].y, -ang[j].s * A[j].y));
 }
 
-// grid = (n_slabs * n_chunks, batch), block = NT (multiple of 32, NT >= G * (Qc + 2)); dynamic smem = 8 * NT cplx
+// grid = (n_slabs * n_chunks, batch), block = NT (multiple of 32, NT >= G * (Qc + 2)); dynamic smem = 12 * NT cplx
 template <int NTMAX>
 __global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cplx *xch = reinterpret_cast<cplx *>(smem_raw);  // [2 edges][4 rows][NT]
+    cplx *xch = reinterpret_cast<cplx *>(smem_raw);  // [2 edges + the upper straddling pair's cos/sin][4 rows][NT]
 
     const int tid = threadIdx.x, NT = blockDim.x;
     const int G = p.G, T = p.T, L = p.L;
@@ -194,9 +219,9 @@ __global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
     // ---- stage 1: h2 (reversed) on (0,1), (2,3) with s_a ----
     {
         Trig ang[5];
-        slab_angles<5>(ang, z, sa * coef(p.cl2, l0));
+        slab_h2_angles(ang, z, sa * coef(p.cl2, l0));
         slab_h2<true>(X[0], X[1], ang, has_prev, has_next);
-        slab_angles<5>(ang, z, sa * coef(p.cl2, l0 + 2));
+        slab_h2_angles(ang, z, sa * coef(p.cl2, l0 + 2));
         slab_h2<true>(X[2], X[3], ang, has_prev, has_next);
     }
     // ---- stages 2 and 4: odd l-pairs; stage 3 in between ----
@@ -204,10 +229,13 @@ __global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         const double s = pass == 0 ? sa : sb;
+        Trig ang_up[4];  // pair (l0 + 3, l0 + 4): evaluated here, handed to the next quad's thread with the edge channel
+        slab_angles<4>(ang_up, v, s * coef(p.cl, l0 + 3));
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             xch[(0 * 4 + j) * NT + tid] = X[0][j];
             xch[(1 * 4 + j) * NT + tid] = X[3][j];
+            xch[(2 * 4 + j) * NT + tid] = c_make(ang_up[j].c, ang_up[j].s);
         }
         __syncthreads();
         {
@@ -217,19 +245,20 @@ __global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
         }
         if (ql > 0) {  // pair (l0 - 1, l0): my channel 0 is the upper member
             cplx nb[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) nb[j] = xch[(1 * 4 + j) * NT + dn];
             Trig ang[4];
-            slab_angles<4>(ang, v, s * coef(p.cl, l0 - 1));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                nb[j] = xch[(1 * 4 + j) * NT + dn];
+                const cplx t = xch[(2 * 4 + j) * NT + dn];
+                ang[j].c = t.x, ang[j].s = t.y;
+            }
             slab_rot_upper(nb, X[0], ang);
         }
         if (up < NT) {  // pair (l0 + 3, l0 + 4): my channel 3 is the lower member
             cplx nb[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) nb[j] = xch[(0 * 4 + j) * NT + up];
-            Trig ang[4];
-            slab_angles<4>(ang, v, s * coef(p.cl, l0 + 3));
-            slab_rot_lower(X[3], nb, ang);
+            slab_rot_lower(X[3], nb, ang_up);
         }
         if (pass == 0) {
             // ---- stage 3: even l-pairs by s_a + s_b, mask ----
@@ -249,9 +278,9 @@ __global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
     // ---- stage 5: h2 (forward) on (0,1), (2,3) with s_b ----
     {
         Trig ang[5];
-        slab_angles<5>(ang, z, sb * coef(p.cl2, l0));
+        slab_h2_angles(ang, z, sb * coef(p.cl2, l0));
         slab_h2<false>(X[0], X[1], ang, has_prev, has_next);
-        slab_angles<5>(ang, z, sb * coef(p.cl2, l0 + 2));
+        slab_h2_angles(ang, z, sb * coef(p.cl2, l0 + 2));
         slab_h2<false>(X[2], X[3], ang, has_prev, has_next);
     }
 
