@@ -146,6 +146,15 @@ ION_DEVINL void fast_sincos_n(const double (&theta)[N], double (&sn)[N], double 
 ION_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 ION_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// 16-byte asynchronous global -> shared copies (LDGSTS), used to stage the LU factors during the prologue
+ION_DEVINL void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+ION_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+ION_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // 128-bit global accesses of one complex128
 ION_DEVINL cplx ld_c(const cplx *p) { return *p; }
 ION_DEVINL void st_c(cplx *p, cplx v) { *p = v; }

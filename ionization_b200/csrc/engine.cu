@@ -229,12 +229,19 @@ void prof_end(ion_sim *s)
     s->ev_kind.push_back(-1);
 }
 
-size_t unit_smem_bytes(const ion_sim *s) { return (256 + 4 * (size_t)s->Tc) * sizeof(cplx); }
+// scan scratch + r-pair exchange; the Crank-Nicolson pair programs also stage the LU factors of both channels (layout 2)
+size_t unit_smem_bytes(const ion_sim *s, int prog = -1)
+{
+    size_t n = (256 + 4 * (size_t)s->Tc) * sizeof(cplx);
+    const bool cn_pair = (prog == ion::PROG_ROT_CN_ROT || prog == ion::PROG_H2_CN_H2 || prog < 0);
+    if (cn_pair && s->M == 4 && s->S == 1 && s->tmax <= 512) n += 8 * (size_t)s->Tc * sizeof(cplx) + 9 * (size_t)(s->Tc / 2) * sizeof(double);
+    return n;
+}
 
 template <int PROG>
 int launch_unit_prog(ion_sim *s, const ion::UnitParams &p, dim3 grid)
 {
-    const size_t smem = unit_smem_bytes(s);
+    const size_t smem = unit_smem_bytes(s, PROG);
     const dim3 block(PROG == ion::PROG_ROT ? s->T_seg : s->Tc);
     // programmatic dependent launch: the kernel's psi-independent prologue overlaps the previous kernel's tail
     cudaLaunchConfig_t cfg;
@@ -267,6 +274,10 @@ template <int PROG>
 int set_unit_smem_attr()
 {
     CUDA_TRY(cudaFuncSetAttribute(ion::k_unit<4, PROG, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    if (PROG == ion::PROG_ROT_CN_ROT || PROG == ion::PROG_H2_CN_H2) {
+        CUDA_TRY(cudaFuncSetAttribute(ion::k_unit<4, PROG, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(ion::k_unit<4, PROG, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    }
     return ION_OK;
 }
 // kernels launched with more than 48 KB of dynamic shared memory (T > 704) need the opt-in; done once at creation,

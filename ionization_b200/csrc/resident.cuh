@@ -108,112 +108,6 @@ ION_DEVINL void ll_recv(const uint4 *box, int T, cplx (&v)[4], unsigned seq, LLS
         v[k] = c_make(__hiloint2double((int)u[2 * k].z, (int)u[2 * k].x), __hiloint2double((int)u[2 * k + 1].z, (int)u[2 * k + 1].x));
 }
 
-// ---------------------------------------------------------------------------------------------
-// Affine scan over the lanes of the same residue class mod STRIDE (layout 2: STRIDE = 2 channels interleaved).
-// Thread carries f(v) = P v + B over its chunk; returns the value entering the chunk.  smP/smB: 32 cplx each.
-// ---------------------------------------------------------------------------------------------
-template <bool FWD, int STRIDE>
-ION_DEVINL cplx affine_scan_strided_exclusive(cplx P, cplx B, cplx *smP, cplx *smB, int tid, int nthreads, int reach)
-{
-    const int lane = tid & 31, warp = tid >> 5, nw = nthreads >> 5, c = lane % STRIDE;
-#pragma unroll
-    for (int s = STRIDE; s < 32; s <<= 1) {
-        cplx Pp = FWD ? shfl_up_c(P, s) : shfl_down_c(P, s);
-        cplx Bp = FWD ? shfl_up_c(B, s) : shfl_down_c(B, s);
-        const bool act = FWD ? (lane >= s) : (lane + s < 32);
-        if (act) {
-            B = c_fma(P, Bp, B);
-            P = c_mul(P, Pp);
-        }
-    }
-    cplx win = c_zero();
-    if (nw > 1) {
-        if (FWD ? (lane >= 32 - STRIDE) : (lane < STRIDE)) {
-            smP[warp * STRIDE + c] = P;
-            smB[warp * STRIDE + c] = B;
-        }
-        __syncthreads();
-        const int depth = reach > 0 ? reach + 1 : nw;
-#pragma unroll 1
-        for (int j = depth; j >= 1; --j) {
-            const int src = FWD ? warp - j : warp + j;
-            if (src >= 0 && src < nw) win = c_fma(smP[src * STRIDE + c], win, smB[src * STRIDE + c]);
-        }
-    }
-    cplx Pe = FWD ? shfl_up_c(P, STRIDE) : shfl_down_c(P, STRIDE);
-    cplx Be = FWD ? shfl_up_c(B, STRIDE) : shfl_down_c(B, STRIDE);
-    const bool first = FWD ? (lane < STRIDE) : (lane >= 32 - STRIDE);
-    return first ? win : c_fma(Pe, win, Be);
-}
-
-// layout 1 -> layout 2 for the channel pair (X, Y): the even lane of a lane pair ends up with rows 8p .. 8p+7 of X,
-// the odd lane with the same rows of Y
-ION_DEVINL void pair_transpose_in(const cplx (&X)[4], const cplx (&Y)[4], cplx (&Z)[8], bool odd)
-{
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const cplx give = odd ? X[k] : Y[k];
-        const cplx got = make_double2(__shfl_xor_sync(0xffffffffu, give.x, 1), __shfl_xor_sync(0xffffffffu, give.y, 1));
-        Z[k] = odd ? got : X[k];
-        Z[4 + k] = odd ? Y[k] : got;
-    }
-}
-ION_DEVINL void pair_transpose_out(const cplx (&Z)[8], cplx (&X)[4], cplx (&Y)[4], bool odd)
-{
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const cplx give = odd ? Z[k] : Z[4 + k];
-        const cplx got = make_double2(__shfl_xor_sync(0xffffffffu, give.x, 1), __shfl_xor_sync(0xffffffffu, give.y, 1));
-        X[k] = odd ? got : Z[k];
-        Y[k] = odd ? Z[4 + k] : got;
-    }
-}
-
-// Crank-Nicolson on the 8 consecutive rows of one channel held by this thread (layout 2).
-//   wcol: this thread's column of the LU factors in shared memory, row k at wcol[k * T]
-//   tocol: tau*off of the thread's rows in shared memory (row k at tocol[k * T/2], the row before the chunk at k = 8)
-//   wprev: LU factor of the row before the chunk (0 at the channel start)
-//   Pt, Qt: chunk multipliers (forward: e_{-1} e_0 .. e_6, backward: e_0 .. e_7)
-ION_DEVINL cplx e_of(double to, cplx w) { return c_make(to * w.y, -to * w.x); }  // -i * to * w
-
-ION_DEVINL void cn8(cplx (&g)[8], const cplx *wcol, int T, const double *tocol, cplx wprev, cplx Pt, cplx Qt, int tid, int nthreads,
-                    cplx *sm, int reach)
-{
-    const int TH = T >> 1;  // tocol[k * TH]: tau*off of row k of the chunk, k = 8: of the row before the chunk
-#define to_(k) tocol[(k) * TH]
-    // forward, zero inflow
-    cplx z = g[0];
-#pragma unroll
-    for (int k = 1; k < 8; ++k) z = c_fma(e_of(to_(k - 1), wcol[(k - 1) * T]), z, g[k]);
-    const cplx yin = affine_scan_strided_exclusive<true, 2>(Pt, z, sm, sm + 32, tid, nthreads, reach);
-    // forward, true inflow; u = w * y
-    cplx u[8];
-    cplx wk = wcol[0];
-    cplx y = c_fma(e_of(to_(8), wprev), yin, g[0]);
-    u[0] = c_mul(wk, y);
-#pragma unroll
-    for (int k = 1; k < 8; ++k) {
-        const cplx e = e_of(to_(k - 1), wk);
-        wk = wcol[k * T];
-        y = c_fma(e, y, g[k]);
-        u[k] = c_mul(wk, y);
-    }
-    // backward, zero inflow
-    z = u[7];
-#pragma unroll
-    for (int k = 6; k >= 0; --k) z = c_fma(e_of(to_(k), wcol[k * T]), z, u[k]);
-    const cplx xin = affine_scan_strided_exclusive<false, 2>(Qt, z, sm + 64, sm + 96, tid, nthreads, reach);
-    // backward, true inflow; out = 2 x - g
-    cplx x = c_fma(e_of(to_(7), wcol[7 * T]), xin, u[7]);
-    g[7] = c_make(fma(2.0, x.x, -g[7].x), fma(2.0, x.y, -g[7].y));
-#pragma unroll
-    for (int k = 6; k >= 0; --k) {
-        x = c_fma(e_of(to_(k), wcol[k * T]), x, u[k]);
-        g[k] = c_make(fma(2.0, x.x, -g[k].x), fma(2.0, x.y, -g[k].y));
-    }
-#undef to_
-}
-
 // upper / lower member only of an l-pair rotation (the straddling pairs: the partner belongs to the neighbour CTA)
 template <bool REAL>
 ION_DEVINL void rotate_upper_only(const cplx (&A)[4], cplx (&B)[4], const RotAngles<4> &ang)  // B = upper member (l+1)
