@@ -59,11 +59,12 @@ enum KernelKind : int {
     KK_OBSERVE,
     KK_RESIDENT,
     KK_SLAB,
+    KK_LEN_STEP,
     KK_COUNT
 };
 const char *const kKernelNames[KK_COUNT] = {"rot",        "rot_cn_rot", "h2",        "h2_cn_h2", "cn",     "line_so_len",
                                             "line_so_vel", "line_cn",    "sweep_flat", "mask",    "observe",
-                                            "resident",    "slab"};
+                                            "resident",    "slab",       "len_step"};
 
 template <typename T>
 int dev_alloc(T **p, size_t n)
@@ -98,6 +99,8 @@ struct ion_sim {
     cplx *psi2 = nullptr, *psi_home = nullptr;
     bool use_slab = true;
     int slab_state = 0;  // 0: not examined, 1: usable, -1: not usable
+    bool use_len_fold = true;
+    int len_fold_state = 0;  // length gauge: even sweep folded into the out-of-place PROG_LEN_STEP kernel (0 / 1 / -1 as above)
     int slab_G = 0, slab_slabs = 0, slab_chunks = 0, slab_Qc = 0, slab_nQ = 0, slab_threads = 0;
     cplx *h_diag = nullptr;
     double *h_off = nullptr;
@@ -233,7 +236,7 @@ void prof_end(ion_sim *s)
 size_t unit_smem_bytes(const ion_sim *s, int prog = -1)
 {
     size_t n = (256 + 4 * (size_t)s->Tc) * sizeof(cplx);
-    const bool cn_pair = (prog == ion::PROG_ROT_CN_ROT || prog == ion::PROG_H2_CN_H2 || prog < 0);
+    const bool cn_pair = (prog == ion::PROG_ROT_CN_ROT || prog == ion::PROG_H2_CN_H2 || prog == ion::PROG_LEN_STEP || prog < 0);
     if (cn_pair && s->M == 4 && s->S == 1 && s->tmax <= 512) n += 8 * (size_t)s->Tc * sizeof(cplx) + 9 * (size_t)(s->Tc / 2) * sizeof(double);
     return n;
 }
@@ -274,7 +277,7 @@ template <int PROG>
 int set_unit_smem_attr()
 {
     CUDA_TRY(cudaFuncSetAttribute(ion::k_unit<4, PROG, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    if (PROG == ion::PROG_ROT_CN_ROT || PROG == ion::PROG_H2_CN_H2) {
+    if (PROG == ion::PROG_ROT_CN_ROT || PROG == ion::PROG_H2_CN_H2 || PROG == ion::PROG_LEN_STEP) {
         CUDA_TRY(cudaFuncSetAttribute(ion::k_unit<4, PROG, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(ion::k_unit<4, PROG, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
     }
@@ -289,7 +292,8 @@ int prepare_kernels(ion_sim *s)
     if ((rc = set_unit_smem_attr<ion::PROG_ROT>()) || (rc = set_unit_smem_attr<ion::PROG_ROT_CN_ROT>()) ||
         (rc = set_unit_smem_attr<ion::PROG_H2>()) || (rc = set_unit_smem_attr<ion::PROG_H2_CN_H2>()) ||
         (rc = set_unit_smem_attr<ion::PROG_CN>()) || (rc = set_unit_smem_attr<ion::PROG_LINE_SO_LEN>()) ||
-        (rc = set_unit_smem_attr<ion::PROG_LINE_SO_VEL>()) || (rc = set_unit_smem_attr<ion::PROG_LINE_CN>()))
+        (rc = set_unit_smem_attr<ion::PROG_LINE_SO_VEL>()) || (rc = set_unit_smem_attr<ion::PROG_LINE_CN>()) ||
+        (rc = set_unit_smem_attr<ion::PROG_LEN_STEP>()))
         return rc;
     return ION_OK;
 }
@@ -299,6 +303,7 @@ ion::UnitParams base_params(ion_sim *s)
     ion::UnitParams p;
     std::memset(&p, 0, sizeof(p));
     p.psi = s->psi;
+    p.psi_out = s->psi;
     p.w = s->w;
     p.aggP = s->aggP;
     p.aggQ = s->aggQ;
@@ -381,6 +386,13 @@ int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, c
             kind = KK_LINE_CN;
             prof_begin(s, kind);
             rc = launch_unit_prog<ion::PROG_LINE_CN>(s, p, grid);
+            break;
+        case ion::PROG_LEN_STEP:
+            kind = KK_LEN_STEP;
+            p.psi_out = s->psi2;
+            prof_begin(s, kind);
+            rc = launch_unit_prog<ion::PROG_LEN_STEP>(s, p, grid);
+            std::swap(s->psi, s->psi2);
             break;
         default: return fail(ION_EINVAL, "unknown unit program");
     }
@@ -502,6 +514,29 @@ bool fast_l_path(const ion_sim *s) { return (s->L_total % 2) == 0; }
 // velocity-gauge inter-solve kernel (slab.cuh): one out-of-place pass replaces the five pair-local passes between two
 // Crank-Nicolson solves.  Decided once per handle: split-operator velocity gauge, even l_bound, unsharded, M = 4, S = 1.
 // ---------------------------------------------------------------------------------------------
+int ensure_second_buffer(ion_sim *s)
+{
+    if (s->psi2) return ION_OK;
+    const size_t n = (size_t)s->batch * s->L * s->Rp;
+    if (int rc = dev_alloc(&s->psi2, n)) return rc;
+    CUDA_TRY(cudaMemsetAsync(s->psi2, 0, n * sizeof(cplx), s->stream));  // the padding rows are never written by the slab kernel
+    s->psi_home = s->psi;
+    return ION_OK;
+}
+
+// length gauge: the even sweep (tail of step n-1, mask, head of step n) is folded into the odd-pair Crank-Nicolson kernel,
+// which reads the even-pair partners of its two channels read-only and therefore works out of place: one pass per step.
+int len_fold_prepare(ion_sim *s)
+{
+    if (s->len_fold_state != 0) return ION_OK;
+    s->len_fold_state = -1;
+    if (!s->use_len_fold || s->program != ION_SH_LEN_SO || !fast_l_path(s)) return ION_OK;
+    if (s->L_own != s->L_total || s->L < 2) return ION_OK;
+    if (int rc = ensure_second_buffer(s)) return rc;
+    s->len_fold_state = 1;
+    return ION_OK;
+}
+
 int slab_prepare(ion_sim *s)
 {
     if (s->slab_state != 0) return ION_OK;
@@ -529,11 +564,8 @@ int slab_prepare(ion_sim *s)
     s->slab_chunks = chunks;
     s->slab_slabs = s->R / W + 1;
     s->slab_threads = (G * loaded + 31) / 32 * 32;
-    const size_t n = (size_t)s->batch * s->L * s->Rp;
-    if (int rc = dev_alloc(&s->psi2, n)) return rc;
-    CUDA_TRY(cudaMemsetAsync(s->psi2, 0, n * sizeof(cplx), s->stream));  // the padding rows are never written
+    if (int rc = ensure_second_buffer(s)) return rc;
     CUDA_TRY(cudaFuncSetAttribute(ion::k_slab<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 512 * (int)sizeof(cplx)));
-    s->psi_home = s->psi;
     s->slab_state = 1;
     return ION_OK;
 }
@@ -599,6 +631,11 @@ int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, int pre, b
     int rc = ION_OK;
     switch (s->program) {
         case ION_SH_LEN_SO:
+            if (fast_l_path(s) && s->len_fold_state == 1) {
+                // the previous step's deferred tail (its scalar is the row before sa), the mask and this step's head ride along
+                if ((rc = launch_unit(s, PROG_LEN_STEP, 1, pre ? F_MASK : 0, sa, pre ? sa - s->batch : nullptr))) return rc;
+                return fuse_next ? ION_OK : launch_unit(s, PROG_ROT, 0, F_MASK, sa, nullptr);
+            }
             if (fast_l_path(s)) {
                 if (pre < 1 && (rc = launch_unit(s, PROG_ROT, 0, 0, sa, nullptr))) return rc;
                 if ((rc = launch_unit(s, PROG_ROT_CN_ROT, 1, 0, sa, nullptr))) return rc;
@@ -652,14 +689,15 @@ int check_ready(ion_sim *s)
 
 int upload_scalars(ion_sim *s, int64_t n_steps, const double *taus, const double *fields)
 {
-    size_t need = (size_t)(n_steps + 1) * s->batch;
+    // row 0 and row n_steps + 1 are zero: "the step before the first" / "the step after the last"; step n is row n + 1
+    size_t need = (size_t)(n_steps + 2) * s->batch;
     if (need > s->scal_cap) {
         if (int rc = dev_alloc(&s->scal, need)) return rc;
         s->scal_cap = need;
     }
     std::vector<double> h(need, 0.0);
     for (int64_t n = 0; n < n_steps; ++n)
-        for (int b = 0; b < s->batch; ++b) h[(size_t)n * s->batch + b] = taus[n] * fields[(size_t)n * s->batch + b];
+        for (int b = 0; b < s->batch; ++b) h[(size_t)(n + 1) * s->batch + b] = taus[n] * fields[(size_t)n * s->batch + b];
     CUDA_TRY(cudaMemcpyAsync(s->scal, h.data(), need * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));  // h goes out of scope
     return ION_OK;
@@ -879,6 +917,7 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
 
     if (int rc = resident_prepare(s)) return rc;
     if (int rc = slab_prepare(s)) return rc;
+    if (int rc = len_fold_prepare(s)) return rc;
     if (s->resident_state == 1 && uniform_tau) {
         // on-chip resident kernel: one persistent launch per stretch between observations
         if (int rc = ensure_factor(s, taus[0])) return rc;
@@ -886,7 +925,7 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
         for (int64_t n = 0; n < n_steps; ++n) {
             const bool obs = observe_mask && observe_mask[n];
             if (!obs && n + 1 < n_steps) continue;
-            if (int rc = launch_resident(s, s->scal + (size_t)n0 * s->batch, n + 1 - n0)) return rc;
+            if (int rc = launch_resident(s, s->scal + (size_t)(n0 + 1) * s->batch, n + 1 - n0)) return rc;
             n0 = n + 1;
             if (obs) {
                 if (int rc = launch_observe(s, what, s->obs_out + (size_t)k_obs * rec)) return rc;
@@ -900,7 +939,7 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
             if (int rc = ensure_factor(s, taus[n])) return rc;
             const bool obs = observe_mask && observe_mask[n];
             const bool fuse_next = can_fuse && (n + 1 < n_steps) && !obs;
-            const double *sa = s->scal + (size_t)n * s->batch;
+            const double *sa = s->scal + (size_t)(n + 1) * s->batch;
             if (int rc = enqueue_step(s, sa, sa + s->batch, pre_done ? fuse_level(s) : 0, fuse_next)) return rc;
             pre_done = fuse_next;
             if (obs) {
@@ -912,7 +951,7 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
     } else {
         if (int rc = ensure_factor(s, taus[0])) return rc;
         if (!s->scal_chunk)
-            if (int rc = dev_alloc(&s->scal_chunk, (size_t)(GRAPH_CHUNK + 1) * s->batch)) return rc;
+            if (int rc = dev_alloc(&s->scal_chunk, (size_t)(GRAPH_CHUNK + 2) * s->batch)) return rc;
         if (n_obs && s->obs_chunk_cap < (size_t)GRAPH_CHUNK * rec) {
             s->invalidate_graphs();
             if (int rc = dev_alloc(&s->obs_chunk, (size_t)GRAPH_CHUNK * rec)) return rc;
@@ -942,7 +981,7 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
                 const int64_t before = s->launch_count;
                 CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
                 s->capturing = true;
-                int rc = enqueue_steps(s, len, s->scal_chunk, pattern, pre_done, fuse_last, what, s->obs_chunk, rec, &pre_done_after);
+                int rc = enqueue_steps(s, len, s->scal_chunk + s->batch, pattern, pre_done, fuse_last, what, s->obs_chunk, rec, &pre_done_after);
                 s->capturing = false;
                 cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
                 entry.launches = s->launch_count - before;
@@ -965,7 +1004,7 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
                 }
                 pre_done_after = pd;
             }
-            CUDA_TRY(cudaMemcpyAsync(s->scal_chunk, s->scal + (size_t)n0 * s->batch, (size_t)(len + 1) * s->batch * sizeof(double),
+            CUDA_TRY(cudaMemcpyAsync(s->scal_chunk, s->scal + (size_t)n0 * s->batch, (size_t)(len + 2) * s->batch * sizeof(double),
                                      cudaMemcpyDeviceToDevice, s->stream));
             CUDA_TRY(cudaGraphLaunch(it->second.exec, s->stream));
             s->launch_count += it->second.launches;
@@ -1118,6 +1157,7 @@ int ion_sim_create_sharded(int program, int64_t L_total, int64_t l_begin, int64_
     if (const char *env = std::getenv("ION_RESIDENT")) s->use_resident = (env[0] == '1');
     if (const char *env = std::getenv("ION_NO_RESIDENT")) s->use_resident = s->use_resident && !(env[0] == '1');
     if (const char *env = std::getenv("ION_NO_SLAB")) s->use_slab = !(env[0] == '1');
+    if (const char *env = std::getenv("ION_NO_LEN_FOLD")) s->use_len_fold = !(env[0] == '1');
     int rc = prepare_kernels(s);
     if (rc == ION_OK) rc = dev_alloc(&s->psi, (size_t)batch * L * s->Rp);
     if (rc == ION_OK) {

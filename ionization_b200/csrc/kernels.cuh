@@ -27,6 +27,7 @@ enum : int {
 
 struct UnitParams {
     cplx *psi;               // [batch][L][M][T]
+    cplx *psi_out;           // where the results go: psi itself except for the out-of-place PROG_LEN_STEP
     const cplx *w;           // [L][M][T]   1/pivot of (1 + i tau H0), permuted      (k_factor)
     const cplx *aggP;        // [L][T]      forward chunk multipliers
     const cplx *aggQ;        // [L][T]      backward chunk multipliers
@@ -453,7 +454,28 @@ enum : int {
     PROG_LINE_SO_LEN = 5,// exp(-i s w_z) * CN * exp(-i s w_z) [+ mask]             -- LineMesh SO length gauge
     PROG_LINE_SO_VEL = 6,// r-pair rotations even, odd, CN, odd, even [+ mask]      -- LineMesh SO velocity gauge
     PROG_LINE_CN = 7,    // CN with H = H0 + diag(s w_z): pivots rebuilt every step     -- LineMesh CN (ADI) length gauge
+    PROG_LEN_STEP = 8,   // even rotation(s_a + s_b) [+ mask] of the unit's channels with their READ-ONLY even-pair partners,
+                         // then rotation(s_a), CN, rotation(s_a) on the odd pair; out of place -- one pass per LEN step
 };
+
+// One member of an l-pair rotation [[c, -i s], [-i s, c]] (the matrix is symmetric: both members use the same formula)
+template <int M>
+ION_DEVINL void rotate_member(cplx (&X)[M], const cplx (&partner)[M], const RotAngles<M> &ang)
+{
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        const cplx x = X[k], q = partner[k];
+        X[k] = c_make(fma(ang.c[k], x.x, ang.s[k] * q.y), fma(ang.c[k], x.y, -ang.s[k] * q.x));
+    }
+}
+// even-pair partner of local channel c: (index, coefficient index) -- channel c with GLOBAL index gl pairs with gl^1
+ION_DEVINL bool even_partner(const UnitParams &p, int c, int &pc, int &ci)
+{
+    const int gl = p.l_begin + c;
+    pc = (gl & 1) ? c - 1 : c + 1;
+    ci = (gl & 1) ? gl - 1 : gl;
+    return pc >= 0 && pc < p.L;
+}
 
 // ---------------------------------------------------------------------------------------------
 // LU factors of (1 + i tau (H0 + diag(E w_z))) built on the fly (LineMesh Crank-Nicolson in the length gauge:
@@ -617,7 +639,8 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
 
     // ---- programs containing Crank-Nicolson ----
     // pairs: both channels are solved together in layout 2 (see above); single channels and r-segments keep layout 1
-    constexpr bool L2CN = (M == 4) && !SEG && (TMAX <= 512) && (PROG == PROG_ROT_CN_ROT || PROG == PROG_H2_CN_H2);
+    constexpr bool L2CN = (M == 4) && !SEG && (TMAX <= 512) && (PROG == PROG_ROT_CN_ROT || PROG == PROG_H2_CN_H2 || PROG == PROG_LEN_STEP);
+    cplx *obase = p.psi_out + ((size_t)b * p.L + l0) * chan;
     if constexpr (L2CN) if (pair) {
         cplx *wsm = xs + 4 * Tc;                                  // [8][Tc]   LU factors, row k of the thread's chunk at wsm[k * Tc + tl]
         double *tosm = reinterpret_cast<double *>(wsm + 8 * Tc);  // [9][Tc/2] tau*off of the chunk's rows (+ the row before it)
@@ -644,12 +667,16 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
             P8 = c_mul(ld_c(p.aggP + ch), ld_c(p.aggP + ch + 1));
             Q8 = c_mul(ld_c(p.aggQ + ch), ld_c(p.aggQ + ch + 1));
         }
-        RotAngles<M> rang;
+        RotAngles<M> rang, eangA, eangB;
         RPairAngles<M> pang;
-        if (PROG == PROG_ROT_CN_ROT) {
+        if (PROG == PROG_ROT_CN_ROT || PROG == PROG_LEN_STEP) {
             double vec[M];
             load_vec<M>(vec, p.vec, T, t, true);
             rang = rot_angles<M>(vec, sa * p.cl[p.l_begin + l0]);
+            if (PROG == PROG_LEN_STEP) {  // a pair always has both even-pair partners: l0 - 1 and l0 + 2
+                eangA = rot_angles<M>(vec, (sa + sb) * p.cl[p.l_begin + l0 - 1]);
+                eangB = rot_angles<M>(vec, (sa + sb) * p.cl[p.l_begin + l0 + 1]);
+            }
         } else {
             double zv[M];
             load_vec<M>(zv, p.zvec, T, t, true);
@@ -658,7 +685,23 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         pdl_wait();
         load_rows<M>(A, base, T, t, true);
         load_rows<M>(B, base + chan, T, t, true);
-        if (PROG == PROG_ROT_CN_ROT) rotate_pair<M, false>(A, B, rang);
+        if (PROG == PROG_LEN_STEP) {
+            cplx Q[M];
+            load_rows<M>(Q, base - chan, T, t, true);
+            rotate_member<M>(A, Q, eangA);
+            load_rows<M>(Q, base + 2 * chan, T, t, true);
+            rotate_member<M>(B, Q, eangB);
+            if (p.flags & F_MASK) {
+                double mk[M];
+                load_vec<M>(mk, p.mask, T, t, true);
+#pragma unroll
+                for (int k = 0; k < M; ++k) {
+                    A[k] = c_scale(A[k], mk[k]);
+                    B[k] = c_scale(B[k], mk[k]);
+                }
+            }
+        }
+        if (PROG == PROG_ROT_CN_ROT || PROG == PROG_LEN_STEP) rotate_pair<M, false>(A, B, rang);
         else h2_pair<M>(A, B, pang, false, tl, Tc, xs);  // (oe, oo)
         cp_async_wait_all();
         __syncthreads();
@@ -669,10 +712,10 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
             cn8(Z, wsm + tl, Tc, tosm + pp, wprev, P8, Q8, tl, Tc, sm_scan, p.short_scan);
             pair_transpose_out(Z, A, B, odd);
         }
-        if (PROG == PROG_ROT_CN_ROT) rotate_pair<M, false>(A, B, rang);
+        if (PROG == PROG_ROT_CN_ROT || PROG == PROG_LEN_STEP) rotate_pair<M, false>(A, B, rang);
         else h2_pair<M>(A, B, pang, true, tl, Tc, xs);  // (oo, oe)
-        store_rows<M>(A, base, T, t, true);
-        store_rows<M>(B, base + chan, T, t, true);
+        store_rows<M>(A, obase, T, t, true);
+        store_rows<M>(B, obase + chan, T, t, true);
         return;
     }
     double toff[M];
@@ -689,10 +732,25 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
     // trigonometry of the programs that rotate before the solve: also independent of psi
     RotAngles<M> rang;
     RPairAngles<M> pang;
-    if (PROG == PROG_ROT_CN_ROT && pair) {
+    if ((PROG == PROG_ROT_CN_ROT || PROG == PROG_LEN_STEP) && pair) {
         double vec[M];
         load_vec<M>(vec, p.vec, T, t, ok);
         rang = rot_angles<M>(vec, sa * p.cl[p.l_begin + l0]);
+    }
+    // PROG_LEN_STEP: even half-rotations of A (and B) with their read-only even-pair partners
+    RotAngles<M> eangA, eangB;
+    int pcA = -1, pcB = -1;
+    bool haveA = false, haveB = false;
+    if (PROG == PROG_LEN_STEP) {
+        double vec[M];
+        load_vec<M>(vec, p.vec, T, t, ok);
+        int ci;
+        haveA = even_partner(p, l0, pcA, ci);
+        if (haveA) eangA = rot_angles<M>(vec, (sa + sb) * p.cl[ci]);
+        if (pair) {
+            haveB = even_partner(p, l0 + 1, pcB, ci);
+            if (haveB) eangB = rot_angles<M>(vec, (sa + sb) * p.cl[ci]);
+        }
     }
     if (PROG == PROG_H2_CN_H2 && pair) {
         double zv[M];
@@ -702,8 +760,28 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
     pdl_wait();
     load_rows<M>(A, base, T, t, ok);
     if (pair) load_rows<M>(B, base + chan, T, t, ok);
+    if (PROG == PROG_LEN_STEP) {
+        cplx Q[M];
+        if (haveA) {
+            load_rows<M>(Q, base + ((ptrdiff_t)pcA - l0) * (ptrdiff_t)chan, T, t, ok);
+            rotate_member<M>(A, Q, eangA);
+        }
+        if (haveB) {
+            load_rows<M>(Q, base + ((ptrdiff_t)pcB - l0) * (ptrdiff_t)chan, T, t, ok);
+            rotate_member<M>(B, Q, eangB);
+        }
+        if (p.flags & F_MASK) {
+            double mk[M];
+            load_vec<M>(mk, p.mask, T, t, ok);
+#pragma unroll
+            for (int k = 0; k < M; ++k) {
+                A[k] = c_scale(A[k], mk[k]);
+                if (pair) B[k] = c_scale(B[k], mk[k]);
+            }
+        }
+    }
 
-    if (PROG == PROG_ROT_CN_ROT) {
+    if (PROG == PROG_ROT_CN_ROT || PROG == PROG_LEN_STEP) {
         const RotAngles<M> &ang = rang;  // reused after the CN
         if (pair) rotate_pair<M, false>(A, B, ang);
         cn_channel<M>(A, fA, toff, toff_prev, tl, Tc, sm_scan, short_scan);
@@ -786,8 +864,8 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
             for (int k = 0; k < M; ++k) A[k] = c_scale(A[k], mk[k]);
         }
     }
-    store_rows<M>(A, base, T, t, mine);
-    if (pair) store_rows<M>(B, base + chan, T, t, mine);
+    store_rows<M>(A, obase, T, t, mine);
+    if (pair) store_rows<M>(B, obase + chan, T, t, mine);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -352,3 +352,49 @@ def test_velocity_inter_solve_kernel_with_sparse_observations_and_ensemble():
             assert np.max(np.abs(rec[:, b, :] - rec_b[:, 0, :])) < 1e-13
     finally:
         del os.environ["ION_NO_SLAB"]
+
+
+@pytest.mark.parametrize("name,n", [("sh_len_so_100x10", None), ("c1_sh_len_so_500x50", 201), ("known_sh_len_so_500x200", 130)])
+def test_length_gauge_folded_step_matches_two_pass_schedule(name, n, monkeypatch):
+    """PROG_LEN_STEP (even sweep folded into the out-of-place odd-pair Crank-Nicolson kernel: one pass per step)
+    against the two-pass schedule [ROT even] [ROT-CN-ROT odd]"""
+    eng = _engine()
+    p = load_golden(name)
+    n = len(p["taus"]) if n is None else n
+    out = {}
+    for mode in ("folded", "two_pass"):
+        if mode == "two_pass":
+            monkeypatch.setenv("ION_NO_LEN_FOLD", "1")
+        with eng.DeviceSimulation.from_problem(p) as sim:
+            sim.step(p["taus"][:n], p["fields"][:n])
+            out[mode] = sim.read_g()[0]
+            out[mode + "_launches"] = sim.launch_count
+        if mode == "two_pass":
+            monkeypatch.delenv("ION_NO_LEN_FOLD")
+    assert rel_err(out["folded"], out["two_pass"]) < 1e-13
+    assert out["folded_launches"] < out["two_pass_launches"]
+
+
+def test_length_gauge_folded_step_with_sparse_observations_and_ensemble():
+    import os
+
+    eng = _engine()
+    p = load_golden("sh_len_so_datastores_120x12")
+    n = len(p["taus"])
+    fields = np.stack([p["fields"], 0.5 * p["fields"], -1.3 * p["fields"]], axis=1)
+    pattern = np.zeros(n, dtype=np.uint8)
+    pattern[[0, 2, 3, 9, 14, n - 1]] = 1
+    what = eng.nat.OBS_NORM | eng.nat.OBS_INNER_PRODUCTS
+    with eng.DeviceSimulation.from_problem(p, batch=3) as sim:
+        rec = sim.run(p["taus"], fields, pattern, what)
+        g = sim.read_g()
+    os.environ["ION_NO_LEN_FOLD"] = "1"
+    try:
+        for b in range(3):
+            with eng.DeviceSimulation.from_problem(p) as sim:
+                rec_b = sim.run(p["taus"], np.ascontiguousarray(fields[:, b]), pattern, what)
+                g_b = sim.read_g()[0]
+            assert rel_err(g[b], g_b) < 1e-13
+            assert np.max(np.abs(rec[:, b, :] - rec_b[:, 0, :])) < 1e-13
+    finally:
+        del os.environ["ION_NO_LEN_FOLD"]
