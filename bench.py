@@ -333,7 +333,7 @@ def main():
             alg_bytes = BYTES_PER_UPDATE * L * R * batch * steps_per_launch
             achieved = alg_bytes / (dom_ms / dom_n * 1e-3) / 1e9
             roofline = {
-                "bound": "hbm", "kernel": "k_resident" if dom == "resident" else f"k_unit<{dom}>", "time_steps_per_launch": steps_per_launch, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "bound": "hbm", "kernel": "k_resident" if dom == "resident" else ("k_slab" if dom == "slab" else f"k_unit<{dom}>"), "time_steps_per_launch": steps_per_launch, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "avg_launch_us": 1e3 * dom_ms / dom_n, "share_of_step": dom_ms / total_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "kernels_us": {k: round(1e3 * v[0] / v[1], 3) for k, v in prof.items()},

@@ -9,7 +9,7 @@ import sys
 
 def short(name):
     name = name.replace("ion::", "").replace("(int)", "")
-    progs = {"0": "ROT", "1": "ROT_CN_ROT", "2": "H2", "3": "H2_CN_H2", "4": "CN", "5": "LINE_SO_LEN", "6": "LINE_SO_VEL"}
+    progs = {"0": "ROT", "1": "ROT_CN_ROT", "2": "H2", "3": "H2_CN_H2", "4": "CN", "5": "LINE_SO_LEN", "6": "LINE_SO_VEL", "7": "LINE_CN", "8": "LEN_STEP"}
     if name.startswith("void k_unit<") or name.startswith("k_unit<"):
         args = name.split("<")[1].split(">")[0].split(",")
         return f"k_unit<M={args[0].strip()}, {progs.get(args[1].strip(), args[1].strip())}, TMAX={args[2].strip()}>"
