@@ -493,8 +493,10 @@ int ensure_factor(ion_sim *s, double tau)
             CUDA_TRY(cudaGetLastError());
         }
         if (s->S > 1) {
-            // r-segments: the halo must cover the reach (plus one warp of margin for the r-pair edge effects)
-            const int H = 64 * reach;
+            // r-segments: the halo must cover the reach; programs with r-pair bricks (velocity gauge) get one more warp of
+            // margin per unit of reach for the brick edge effects
+            const bool bricks = (s->program == ION_SH_VEL_SO || s->program == ION_LINE_VEL_SO);
+            const int H = (bricks ? 64 : 32) * reach;
             if (reach == 0 || s->T_seg + 2 * H > 512)
                 return fail(ION_ENOTSUP,
                             "r_points > 4096 needs the Crank-Nicolson LU multipliers to decay below 1e-30 within the segment halo; this "
@@ -1122,7 +1124,7 @@ int ion_sim_create_sharded(int program, int64_t L_total, int64_t l_begin, int64_
     T = (T + 31) / 32 * 32;
     int S = 1, T_seg = (int)T, H = 0;
     if (T > 1024) {  // r-segments with halos (kernels.cuh); the halo width is fixed when the LU factors are built
-        T_seg = (program == ION_LINE_LEN_CN) ? 256 : 384;
+        T_seg = 384;  // + 2 x 32 halo threads per unit of reach (2 x 64 with r-pair bricks): 448 or 512 threads per CTA
         H = 64;
         S = (int)((T + T_seg - 1) / T_seg);
         T = (int64_t)S * T_seg;
