@@ -168,6 +168,26 @@ int ion_sim_phase_needs_halo(ion_sim_t *sim, int phase);
  * must have delivered the neighbours' send buffers (filled by phase p-1) into this shard's recv buffers. */
 int ion_sim_step_phase(ion_sim_t *sim, int phase, double tau, const double *field);
 
+/* ---- halo exchange over NVLink peer memory, inside the engine (csrc/halo.cuh) ----
+ * Instead of the caller exchanging boundary channels between phases, the shards can be linked once: every shard
+ * exports a blob (CUDA IPC handle of its halo block: flags + two staging slots per side), the caller hands
+ * each shard the blobs of its neighbours (torch.distributed all_gather of ION_PEER_BLOB_BYTES bytes is the only
+ * collective), and from then on ion_sim_step / ion_sim_run advance the shard like an unsharded simulation: before every
+ * odd-parity kernel a small kernel stores the boundary channel straight into the neighbour's staging slot, raises a
+ * flag there, waits for its own flag and moves the received channel into its ghost channel.  Every shard must make the same sequence of calls (the exchange is a
+ * rendezvous).  Replaces the cgo/NCCL-style send/recv the reference would need; the reference itself has no multi-device
+ * path.  same_process != 0: the blob's raw pointers are used (several shards in one process, tests). */
+#define ION_PEER_BLOB_BYTES 96
+int ion_sim_export_peer(ion_sim_t *sim, void *blob, int64_t blob_bytes);
+int ion_sim_attach_peer(ion_sim_t *sim, int side /* 0: lower neighbour, 1: upper */, const void *blob, int64_t blob_bytes,
+                        int same_process);
+/* one exchange outside a step (e.g. before observing <z>, which couples the last owned channel to the upper ghost) */
+int ion_sim_exchange_halos(ion_sim_t *sim);
+/* build the LU factors for tau now (everything that allocates), so that later steps only launch kernels */
+int ion_sim_prepare(ion_sim_t *sim, double tau);
+/* exchanges completed so far; aborted != 0: a hand-shake timed out (a neighbour never arrived), the state is invalid */
+int ion_sim_halo_status(ion_sim_t *sim, int64_t *exchanges_done, int *aborted);
+
 /* raw device pointer of the wavefunction in internal layout + its size (for peer copies / checksums) */
 int ion_sim_device_psi(ion_sim_t *sim, void **device_ptr, int64_t *n_bytes);
 

@@ -31,6 +31,7 @@ OBS_H0 = 32
 OBS_NORM_WITHIN = 64
 
 ION_ENODEVICE = -2
+PEER_BLOB_BYTES = 96  # include/ionization_b200.h: ION_PEER_BLOB_BYTES
 
 _lib = None
 
@@ -65,6 +66,11 @@ SIGNATURES = {
     "ion_sim_run": (_i32, [_vp, _i64, _vp, _vp, _vp, _u32, _vp]),
     "ion_sim_synchronize": (_i32, [_vp]),
     "ion_sim_halo_buffer": (_i32, [_vp, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_i64)]),
+    "ion_sim_export_peer": (_i32, [_vp, _vp, _i64]),
+    "ion_sim_attach_peer": (_i32, [_vp, _i32, _vp, _i64, _i32]),
+    "ion_sim_exchange_halos": (_i32, [_vp]),
+    "ion_sim_prepare": (_i32, [_vp, _f64]),
+    "ion_sim_halo_status": (_i32, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_i32)]),
     "ion_sim_num_phases": (_i32, [_vp]),
     "ion_sim_phase_needs_halo": (_i32, [_vp, _i32]),
     "ion_sim_step_phase": (_i32, [_vp, _i32, _f64, _vp]),

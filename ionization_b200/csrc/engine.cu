@@ -26,6 +26,7 @@
 #include "kernels.cuh"
 #include "resident.cuh"
 #include "slab.cuh"
+#include "halo.cuh"
 
 namespace {
 
@@ -60,11 +61,12 @@ enum KernelKind : int {
     KK_RESIDENT,
     KK_SLAB,
     KK_LEN_STEP,
+    KK_HALO,
     KK_COUNT
 };
 const char *const kKernelNames[KK_COUNT] = {"rot",        "rot_cn_rot", "h2",        "h2_cn_h2", "cn",     "line_so_len",
                                             "line_so_vel", "line_cn",    "sweep_flat", "mask",    "observe",
-                                            "resident",    "slab",       "len_step"};
+                                            "resident",    "slab",       "len_step",   "halo"};
 
 template <typename T>
 int dev_alloc(T **p, size_t n)
@@ -99,6 +101,12 @@ struct ion_sim {
     cplx *psi2 = nullptr, *psi_home = nullptr;
     bool use_slab = true;
     int slab_state = 0;  // 0: not examined, 1: usable, -1: not usable
+    // l-block shards: halo exchange over peer memory (halo.cuh)
+    unsigned long long *hflags = nullptr;           // my halo block: HF_COUNT flags, then staging[2 sides][2 slots][Rp]
+    unsigned long long *peer_flags[2] = {nullptr, nullptr};
+    cplx *peer_stage[2] = {nullptr, nullptr};       // the neighbours' staging slots facing this shard (peer mappings)
+    void *peer_ipc_base[2] = {nullptr, nullptr};    // IPC mappings to close
+    bool peers_attached = false;
     bool use_len_fold = true;
     int len_fold_state = 0;  // length gauge: even sweep folded into the out-of-place PROG_LEN_STEP kernel (0 / 1 / -1 as above)
     int slab_G = 0, slab_slabs = 0, slab_chunks = 0, slab_Qc = 0, slab_nQ = 0, slab_threads = 0;
@@ -167,6 +175,9 @@ struct ion_sim {
         if (th) cudaFree(th);
         if (obs_chunk) cudaFree(obs_chunk);
         if (halo) cudaFree(halo);
+        for (void *q : peer_ipc_base)
+            if (q) cudaIpcCloseMemHandle(q);
+        if (hflags) cudaFree(hflags);
         if (abort_flag) cudaFree(abort_flag);
         for (auto &g : graphs)
             if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
@@ -345,6 +356,12 @@ int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, c
     }
     dim3 grid(units * s->S, s->batch);
     if (prog == ion::PROG_ROT) p.H = 0;  // point-wise in r: interior threads only
+    // r-segments: a kernel that reads halo rows (every program but the point-wise rotation) must not run in place
+    const bool seg_oop = s->S > 1 && prog != ion::PROG_ROT && prog != ion::PROG_LEN_STEP;
+    if (seg_oop) {
+        if (!s->psi2) return fail(ION_ESTATE, "internal: second wavefunction buffer missing for a segmented kernel");
+        p.psi_out = s->psi2;
+    }
     int rc = ION_OK;
     switch (prog) {
         case ion::PROG_ROT:
@@ -398,6 +415,7 @@ int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, c
     }
     prof_end(s);
     s->launch_count++;
+    if (seg_oop && rc == ION_OK) std::swap(s->psi, s->psi2);
     return rc;
 }
 
@@ -621,6 +639,34 @@ int restore_home(ion_sim *s)
     return ION_OK;
 }
 
+// l-block shard with attached neighbours: deliver the boundary channels into the neighbours' ghosts (halo.cuh)
+int launch_exchange(ion_sim *s)
+{
+    if (!s->peers_attached) return ION_OK;
+    ion::HaloParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.flags = s->hflags;
+    const size_t chan = (size_t)s->Rp;
+    cplx *stage = reinterpret_cast<cplx *>(s->hflags + ion::HF_COUNT);
+    for (int side = 0; side < 2; ++side) {
+        p.peer_flags[side] = s->peer_flags[side];
+        p.peer_stage[side] = s->peer_stage[side];
+        p.my_stage[side] = stage + (size_t)side * 2 * chan;
+    }
+    p.src[0] = s->psi + (size_t)s->g_lo * chan;
+    p.src[1] = s->psi + (size_t)(s->g_lo + s->L_own - 1) * chan;
+    p.ghost[0] = s->psi;
+    p.ghost[1] = s->psi + (size_t)(s->g_lo + s->L_own) * chan;
+    p.n = (long long)chan;
+    p.spin_limit = 20000000000ll;  // ~10 s of SM clock
+    prof_begin(s, KK_HALO);
+    ion::k_halo_exchange<<<dim3(8, 2), 256, 0, s->stream>>>(p);
+    prof_end(s);
+    s->launch_count++;
+    CUDA_TRY(cudaGetLastError());
+    return ION_OK;
+}
+
 // what a step's tail does of the next step's head when the two are fused (no observation in between)
 int fuse_level(const ion_sim *s) { return s->slab_state == 1 ? 2 : 1; }
 
@@ -640,6 +686,7 @@ int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, int pre, b
             }
             if (fast_l_path(s)) {
                 if (pre < 1 && (rc = launch_unit(s, PROG_ROT, 0, 0, sa, nullptr))) return rc;
+                if ((rc = launch_exchange(s))) return rc;
                 if ((rc = launch_unit(s, PROG_ROT_CN_ROT, 1, 0, sa, nullptr))) return rc;
                 return launch_unit(s, PROG_ROT, 0, F_MASK, sa, fuse_next ? sb_next : nullptr);
             }
@@ -653,16 +700,18 @@ int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, int pre, b
             const bool fast = fast_l_path(s);
             if (fast) {
                 if (pre < 1 && (rc = launch_unit(s, PROG_ROT, 0, F_REAL_ROT, sa, nullptr))) return rc;
-                if (pre < 2 && (rc = launch_unit(s, PROG_ROT, 1, F_REAL_ROT, sa, nullptr))) return rc;
+                if (pre < 2 && ((rc = launch_exchange(s)) || (rc = launch_unit(s, PROG_ROT, 1, F_REAL_ROT, sa, nullptr)))) return rc;
             } else {
                 if ((rc = launch_sweep_flat(s, 0, F_REAL_ROT, sa))) return rc;
                 if ((rc = launch_sweep_flat(s, 1, F_REAL_ROT, sa))) return rc;
             }
             if (pre < 2 && (rc = launch_unit(s, PROG_H2, 0, 0, sa, nullptr))) return rc;   // ee, eo
+            if ((rc = launch_exchange(s))) return rc;
             if ((rc = launch_unit(s, PROG_H2_CN_H2, 1, 0, sa, nullptr))) return rc;        // oe, oo, CN, oo, oe
             if (fast && fuse_next && s->slab_state == 1) return launch_slab(s, sa, sb_next);  // eo ee h1_o h1_e mask | h1_e h1_o ee eo
             if ((rc = launch_unit(s, PROG_H2, 0, F_H2_REVERSE, sa, nullptr))) return rc;   // eo, ee
             if (fast) {
+                if ((rc = launch_exchange(s))) return rc;
                 if ((rc = launch_unit(s, PROG_ROT, 1, F_REAL_ROT, sa, nullptr))) return rc;
                 return launch_unit(s, PROG_ROT, 0, F_REAL_ROT | F_MASK, sa, fuse_next ? sb_next : nullptr);
             }
@@ -899,8 +948,9 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
     if (!taus || !fields) return fail(ION_EINVAL, "taus/fields must not be NULL");
     CUDA_TRY(cudaSetDevice(s->device));
     if (int rc = check_ready(s)) return rc;
-    if (s->L_own != s->L_total)
-        return fail(ION_ESTATE, "an l-block shard is advanced with ion_sim_step_phase (halo exchange between phases)");
+    if (s->L_own != s->L_total && !s->peers_attached)
+        return fail(ION_ESTATE, "an l-block shard is advanced with ion_sim_step_phase (caller-side halo exchange between phases) or, after "
+                                "ion_sim_attach_peer, with ion_sim_step/run (peer-memory exchange inside the engine)");
     int64_t n_obs = 0;
     if (observe_mask)
         for (int64_t n = 0; n < n_steps; ++n) n_obs += observe_mask[n] ? 1 : 0;
@@ -920,6 +970,8 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
     if (int rc = resident_prepare(s)) return rc;
     if (int rc = slab_prepare(s)) return rc;
     if (int rc = len_fold_prepare(s)) return rc;
+    if (s->S > 1)
+        if (int rc = ensure_second_buffer(s)) return rc;  // segmented kernels run out of place
     if (s->resident_state == 1 && uniform_tau) {
         // on-chip resident kernel: one persistent launch per stretch between observations
         if (int rc = ensure_factor(s, taus[0])) return rc;
@@ -1426,6 +1478,110 @@ int ion_sim_halo_buffer(ion_sim_t *s, int which, void **device_ptr, int64_t *n_b
     return ION_OK;
 }
 
+
+/* ---- peer-memory halo exchange between l-block shards (halo.cuh) ---- */
+namespace {
+struct PeerBlob {  // what a shard tells its neighbours (ION_PEER_BLOB_BYTES)
+    cudaIpcMemHandle_t halo;  // 64 bytes: the halo block (flags + staging slots)
+    int64_t channel_elems;    // Rp * batch
+    int64_t has_lo, has_hi;   // neighbours this shard expects
+    uint64_t local_halo;      // raw device pointer, valid inside the exporting process only
+};
+static_assert(sizeof(PeerBlob) == 96, "PeerBlob layout");
+
+size_t halo_block_words(const ion_sim *s) { return (size_t)ion::HF_COUNT + 2 * 2 * (size_t)s->Rp * 2; }  // cplx = 2 words
+
+int ensure_halo_flags(ion_sim *s)
+{
+    if (s->hflags) return ION_OK;
+    if (int rc = dev_alloc(&s->hflags, halo_block_words(s))) return rc;
+    CUDA_TRY(cudaMemset(s->hflags, 0, halo_block_words(s) * sizeof(unsigned long long)));
+    return ION_OK;
+}
+}  // namespace
+
+int ion_sim_export_peer(ion_sim_t *s, void *blob, int64_t blob_bytes)
+{
+    if (!s || !blob) return fail(ION_EINVAL, "NULL argument");
+    if (blob_bytes < (int64_t)sizeof(PeerBlob)) return fail(ION_EINVAL, "blob too small (ION_PEER_BLOB_BYTES)");
+    if (s->L_own == s->L_total) return fail(ION_ESTATE, "not an l-block shard");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (int rc = ensure_halo_flags(s)) return rc;
+    PeerBlob b;
+    std::memset(&b, 0, sizeof(b));
+    CUDA_TRY(cudaIpcGetMemHandle(&b.halo, s->hflags));
+    b.channel_elems = (int64_t)s->Rp;
+    b.has_lo = s->g_lo;
+    b.has_hi = s->g_hi;
+    b.local_halo = (uint64_t)(uintptr_t)s->hflags;
+    std::memcpy(blob, &b, sizeof(b));
+    return ION_OK;
+}
+
+int ion_sim_attach_peer(ion_sim_t *s, int side, const void *blob, int64_t blob_bytes, int same_process)
+{
+    if (!s || !blob) return fail(ION_EINVAL, "NULL argument");
+    if (side < 0 || side > 1) return fail(ION_EINVAL, "side must be 0 (lower neighbour) or 1 (upper neighbour)");
+    if (blob_bytes < (int64_t)sizeof(PeerBlob)) return fail(ION_EINVAL, "blob too small (ION_PEER_BLOB_BYTES)");
+    if ((side == 0 && !s->g_lo) || (side == 1 && !s->g_hi)) return fail(ION_ESTATE, "this shard has no neighbour on that side");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (int rc = ensure_halo_flags(s)) return rc;
+    PeerBlob b;
+    std::memcpy(&b, blob, sizeof(b));
+    if (b.channel_elems != (int64_t)s->Rp) return fail(ION_EINVAL, "the neighbour's radial layout differs from this shard's");
+    // my lower neighbour receives my first channel on ITS upper side, my upper neighbour my last channel on its lower side
+    if ((side == 0 && !b.has_hi) || (side == 1 && !b.has_lo)) return fail(ION_EINVAL, "the neighbour has no ghost channel facing this shard");
+    unsigned long long *pblock = nullptr;
+    if (same_process) {
+        pblock = reinterpret_cast<unsigned long long *>((uintptr_t)b.local_halo);
+    } else {
+        void *q = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&q, b.halo, cudaIpcMemLazyEnablePeerAccess));
+        s->peer_ipc_base[side] = q;
+        pblock = static_cast<unsigned long long *>(q);
+    }
+    const int facing = 1 - side;  // the neighbour's side that faces me
+    s->peer_flags[side] = pblock;
+    s->peer_stage[side] = reinterpret_cast<cplx *>(pblock + ion::HF_COUNT) + (size_t)facing * 2 * s->Rp;
+    s->peers_attached = (!s->g_lo || s->peer_flags[0]) && (!s->g_hi || s->peer_flags[1]);
+    s->invalidate_graphs();
+    return ION_OK;
+}
+
+int ion_sim_exchange_halos(ion_sim_t *s)
+{
+    if (!s) return fail(ION_EINVAL, "sim is NULL");
+    if (!s->peers_attached) return fail(ION_ESTATE, "ion_sim_attach_peer has not been called for every neighbour");
+    CUDA_TRY(cudaSetDevice(s->device));
+    return launch_exchange(s);
+}
+
+int ion_sim_prepare(ion_sim_t *s, double tau)
+{
+    if (!s) return fail(ION_EINVAL, "sim is NULL");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (int rc = check_ready(s)) return rc;
+    if (int rc = ensure_factor(s, tau)) return rc;
+    if (s->S > 1)
+        if (int rc = ensure_second_buffer(s)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return ION_OK;
+}
+
+int ion_sim_halo_status(ion_sim_t *s, int64_t *exchanges_done, int *aborted)
+{
+    if (!s || !exchanges_done || !aborted) return fail(ION_EINVAL, "NULL argument");
+    *exchanges_done = 0;
+    *aborted = 0;
+    if (!s->hflags) return ION_OK;
+    unsigned long long h[ion::HF_COUNT];
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaMemcpy(h, s->hflags, sizeof(h), cudaMemcpyDeviceToHost));
+    *exchanges_done = (int64_t)h[ion::HF_SEQ];
+    *aborted = h[ion::HF_ABORT] != 0ull;
+    return ION_OK;
+}
+
 namespace {
 struct Phase {
     int prog, parity, flags;
@@ -1488,7 +1644,10 @@ int ion_sim_step_phase(ion_sim_t *s, int phase, double tau, const double *field)
         CUDA_TRY(cudaMemcpyAsync(s->scal_phase, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
     }
-    return launch_unit(s, ph[phase].prog, ph[phase].parity, ph[phase].flags, s->scal_phase, nullptr);
+    if (s->S > 1)
+        if (int rc = ensure_second_buffer(s)) return rc;
+    if (int rc = launch_unit(s, ph[phase].prog, ph[phase].parity, ph[phase].flags, s->scal_phase, nullptr)) return rc;
+    return restore_home(s);  // the caller's halo buffers point into the home buffer
 }
 
 int ion_sim_device_psi(ion_sim_t *s, void **device_ptr, int64_t *n_bytes)

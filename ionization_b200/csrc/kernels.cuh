@@ -559,7 +559,9 @@ ION_DEVINL void line_cn_factors(CnFactors<M> &f, const cplx (&D)[M], const doubl
 //
 // r-SEGMENTS.  A channel longer than one CTA can hold (r_points > 4096) is cut into S segments of T_seg threads.
 // Each CTA also computes H halo threads (H*M rows) on either side: the r-pair bricks need their neighbours, and the
-// Crank-Nicolson recurrences are simply started from zero at the edge of the halo.  That is exact to < 1e-30
+// Crank-Nicolson recurrences are simply started from zero at the edge of the halo.  The halo rows of one CTA are the
+// interior rows of another, so every segmented kernel that reads a halo runs OUT OF PLACE (psi -> psi_out, the engine
+// swaps the buffers): in place, a CTA of a later wave would read rows its neighbour has already advanced.  That is exact to < 1e-30
 // because the LU multipliers decay geometrically -- the host verifies (k_scan_bound) that their product over any 32
 // threads is below 1e-30 before it allows S > 1.  Halo results are discarded; only interior threads store.
 template <int M, int PROG, int TMAX, bool SEG>
@@ -626,7 +628,15 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
     }
 
     if (PROG == PROG_H2) {
-        if (!pair) return;
+        cplx *obase = p.psi_out + ((size_t)b * p.L + l0) * chan;
+        if (!pair) {  // nothing to do for an unpaired channel; out of place it still has to reach the other buffer
+            if (p.psi_out != p.psi) {
+                pdl_wait();
+                load_rows<M>(A, base, T, t, mine);
+                store_rows<M>(A, obase, T, t, mine);
+            }
+            return;
+        }
         double zv[M];
         load_vec<M>(zv, p.zvec, T, t, ok);
         double sc = sa * p.cl2[p.l_begin + l0];
@@ -635,8 +645,8 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         load_rows<M>(A, base, T, t, ok);
         load_rows<M>(B, base + chan, T, t, ok);
         h2_pair<M>(A, B, ang, (p.flags & F_H2_REVERSE) != 0, tl, Tc, xs);
-        store_rows<M>(A, base, T, t, mine);
-        store_rows<M>(B, base + chan, T, t, mine);
+        store_rows<M>(A, obase, T, t, mine);
+        store_rows<M>(B, obase + chan, T, t, mine);
         return;
     }
 

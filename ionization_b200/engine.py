@@ -223,6 +223,29 @@ class DeviceSimulation:
         field = nat.as_f64(np.broadcast_to(np.asarray(field, dtype=np.float64), (self.batch,)))
         nat.check(self._lib.ion_sim_step_phase(self._h, phase, float(tau), nat.ptr(field)), "ion_sim_step_phase")
 
+    # -- peer-memory halo exchange inside the engine (csrc/halo.cuh) ------------------------------
+    def export_peer(self) -> bytes:
+        """the blob this shard's neighbours need (CUDA IPC handles + ghost offsets)"""
+        buf = ctypes.create_string_buffer(nat.PEER_BLOB_BYTES)
+        nat.check(self._lib.ion_sim_export_peer(self._h, buf, nat.PEER_BLOB_BYTES), "ion_sim_export_peer")
+        return bytes(buf.raw)
+
+    def attach_peer(self, side: int, blob: bytes, same_process: bool = False):
+        """side 0: the lower neighbour's blob, side 1: the upper neighbour's"""
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        nat.check(self._lib.ion_sim_attach_peer(self._h, int(side), buf, len(blob), 1 if same_process else 0), "ion_sim_attach_peer")
+
+    def exchange_halos(self):
+        nat.check(self._lib.ion_sim_exchange_halos(self._h), "ion_sim_exchange_halos")
+
+    def prepare(self, tau: float):
+        nat.check(self._lib.ion_sim_prepare(self._h, float(tau)), "ion_sim_prepare")
+
+    def halo_status(self):
+        n, ab = ctypes.c_int64(0), ctypes.c_int32(0)
+        nat.check(self._lib.ion_sim_halo_status(self._h, ctypes.byref(n), ctypes.byref(ab)), "ion_sim_halo_status")
+        return int(n.value), bool(ab.value)
+
     def halo_buffer(self, which: int):
         """(device pointer, bytes) of a boundary-channel buffer: 0 send-to-lower, 1 send-to-upper, 2 recv-from-lower,
         3 recv-from-upper (None when that neighbour does not exist)"""

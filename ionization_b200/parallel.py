@@ -8,8 +8,12 @@
 * One very large SphericalHarmonicMesh simulation shards over contiguous l-blocks cut at EVEN channels.  The
   Crank-Nicolson solve (in r) and every even-parity l-pair sweep are local to a shard; only the odd-parity sweeps
   couple the last channel of one shard to the first channel of the next, so before each odd-parity kernel the two
-  boundary channels are exchanged with NCCL send/recv (1 exchange per step in the length gauge, 3 in the velocity
-  gauge; one channel = R * 16 bytes per direction) and both shards evaluate the straddling pair redundantly.
+  boundary channels are exchanged (1 exchange per step in the length gauge, 3 in the velocity gauge; one channel =
+  R * 16 bytes per direction) and both shards evaluate the straddling pair redundantly.  Two transports:
+  ``attach_peers`` + ``step_device`` -- the production path: the engine's own kernel stores the boundary channel into the
+  neighbour's ghost channel over NVLink peer memory (CUDA IPC mapping) with a flag hand-shake, inside the captured step
+  loop, no host or NCCL call per step (csrc/halo.cuh); or ``step(..., exchanger)`` -- NCCL send/recv between phases
+  driven from Python (the baseline the first is measured against).
   Reductions (norm, inner products, expectation values) are per-shard partial sums + one small all-reduce.
 
 ``torch.distributed`` is plumbing only (rendezvous, NCCL p2p, all-reduce); the kernels are the engine's.
@@ -146,6 +150,37 @@ class ShardedSimulation:
         self.n_phases = eng.num_phases
         self.halo_phases = [p for p in range(self.n_phases) if eng.phase_needs_halo(p)]
 
+    # ---- peer-memory halo exchange (the engine's own kernels over NVLink; no NCCL on the data path) --------------
+    def attach_peers(self, group=None):
+        """Collective: every rank exports its CUDA IPC blob, one all_gather distributes them, every rank maps its two
+        neighbours.  Afterwards ``step_device`` / ``engine.run`` advance the shard with the exchange inside the engine."""
+        import torch.distributed as dist
+
+        blobs = [None] * dist.get_world_size(group)
+        dist.all_gather_object(blobs, self.engine.export_peer(), group=group)
+        if self.rank > 0:
+            self.engine.attach_peer(0, blobs[self.rank - 1])
+        if self.rank < self.world - 1:
+            self.engine.attach_peer(1, blobs[self.rank + 1])
+        dist.barrier(group=group)
+        self.peers_attached = True
+
+    @staticmethod
+    def attach_local(shards: Sequence["ShardedSimulation"]):
+        """several shards living in ONE process (tests on a single GPU): raw pointers instead of IPC handles"""
+        blobs = [sh.engine.export_peer() for sh in shards]
+        for i, sh in enumerate(shards):
+            if i > 0:
+                sh.engine.attach_peer(0, blobs[i - 1], same_process=True)
+            if i + 1 < len(shards):
+                sh.engine.attach_peer(1, blobs[i + 1], same_process=True)
+            sh.peers_attached = True
+
+    def step_device(self, taus, fields):
+        """advance len(taus) steps with the device-resident loop (fused kernels, CUDA graphs, halo exchange by the engine's
+        own kernels over peer memory).  Asynchronous; every shard must be advanced by the same number of steps."""
+        self.engine.step(np.atleast_1d(taus), np.atleast_1d(fields))
+
     def make_exchanger(self, group=None) -> HaloExchanger:
         return HaloExchanger(self.rank, self.world, self.send_lo, self.send_hi, self.recv_lo, self.recv_hi, group)
 
@@ -175,8 +210,11 @@ class ShardedSimulation:
     def partial_observation(self, what: int, exchanger: Optional[HaloExchanger] = None):
         """this shard's contribution to the observation record (sums over owned channels; <z> also couples the last
         owned channel to the upper ghost, which must be current: the halos are refreshed first)"""
-        if exchanger is not None and (what & nat.OBS_Z):
-            exchanger.exchange()
+        if what & nat.OBS_Z:
+            if exchanger is not None:
+                exchanger.exchange()
+            elif getattr(self, "peers_attached", False):
+                self.engine.exchange_halos()
         return self.engine.observe(what)[0]
 
     def read_g(self):

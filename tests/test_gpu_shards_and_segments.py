@@ -122,3 +122,132 @@ def test_segmented_line_split_operator_long_mesh():
             sim.step(p["taus"], p["fields"])
             g = sim.read_g()[0, 0]
         assert rel_err(g, ref) < TOL, kind
+
+
+def _run_sharded_device(p, world, n_steps=None, what=0):
+    """the production transport: shards linked with ion_sim_attach_peer, advanced by the device-resident loop with the
+    engine's own halo-exchange kernel (flags + stores into the neighbour's ghost channel).  Several shards in ONE process
+    on one GPU: every shard is driven from its own host thread, as every rank would be from its own process."""
+    import threading
+
+    from ionization_b200 import parallel
+
+    shards = [parallel.ShardedSimulation(p, r, world, device=0, use_torch_stream=False) for r in range(world)]
+    parallel.ShardedSimulation.attach_local(shards)
+    taus, fields = p["taus"][:n_steps], p["fields"][:n_steps]
+    for s in shards:
+        s.engine.prepare(float(taus[0]))  # everything that allocates / frees happens before the first hand-shake
+    errors = []
+
+    def drive(s):
+        try:
+            s.step_device(taus, fields)
+            if what:
+                s.engine.exchange_halos()
+            s.engine.synchronize()
+        except Exception as exc:  # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=drive, args=(s,)) for s in shards]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for s in shards:
+        n_ex, aborted = s.engine.halo_status()
+        assert not aborted and n_ex > 0
+    g = np.concatenate([s.read_g() for s in shards], axis=0)
+    rec = None
+    if what:
+        recs = [s.engine.observe(what)[0] for s in shards]
+        rec = parallel.combine_observations(recs, what, n_states=len(p["state_l"]), l_counts=[s.L for s in shards])
+    for s in shards:
+        s.close()
+    return g, rec
+
+
+@pytest.mark.parametrize("name", ["sh_len_so_100x10", "sh_vel_so_60x8", "sh_vel_so_datastores_120x12"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_memory_halo_exchange_reproduces_reference(name, world):
+    from ionization_b200 import _native as nat
+
+    p = load_golden(name)
+    what = nat.OBS_NORM | nat.OBS_INNER_PRODUCTS | nat.OBS_Z
+    g, rec = _run_sharded_device(p, world, what=what)
+    assert rel_err(g, p["g_final"]) < TOL
+    ns = len(p["state_l"])
+    assert abs(rec[0] - p["norm"][-1]) < TOL
+    if "z_expectation" in p:
+        assert abs(rec[1 + 2 * ns] - p["z_expectation"][-1]) < TOL * abs(p["r_expectation"][-1])
+
+
+@pytest.mark.parametrize("kind", ["LEN", "VEL"])
+def test_peer_memory_halo_exchange_equals_unsharded_run_on_a_larger_mesh(kind):
+    from ionization_b200 import configs, engine
+    from ionization_b200 import units as u
+
+    p = configs.spherical_harmonic_problem(r_bound=60 * u.bohr_radius, r_points=600, l_bound=64, gauge=kind, n_steps=70,
+                                           pulse=configs.sinc_pulse(20 * u.asec, 5 * u.Jcm2), time_initial=-35 * u.asec, time_final=35 * u.asec)
+    with engine.DeviceSimulation.from_problem(p) as sim:
+        sim.step(p["taus"], p["fields"])
+        g_ref = sim.read_g()[0]
+    g, _ = _run_sharded_device(p, 4)
+    assert rel_err(g, g_ref) < 1e-12
+
+
+@pytest.mark.parametrize("kind", ["LEN", "VEL"])
+def test_r_segmented_kernels_with_more_ctas_than_fit_on_the_gpu(kind, monkeypatch):
+    """Regression: the halo rows of one segment's CTA are the interior rows of its neighbour's, so a segmented kernel that
+    ran in place gave wrong results as soon as the grid needed more than one wave of CTAs (a later CTA read rows its
+    neighbour had already advanced).  8192 rows x 64 channels = 6 segments x 33 units = 198 CTAs of 448/512 threads on 148
+    SMs; both the fused single-GPU schedule and the single-sweep schedule the shards use are checked against the oracle."""
+    from ionization_b200 import configs, engine
+    from ionization_b200 import units as u
+    from oracle import cport
+
+    R, L, n = 8192, 64, 24
+    p = configs.spherical_harmonic_problem(r_bound=0.1 * R * u.bohr_radius, r_points=R, l_bound=L, gauge=kind, n_steps=n,
+                                           pulse=configs.sinc_pulse(20 * u.asec, 20 * u.Jcm2), time_initial=-n / 2 * u.asec, time_final=n / 2 * u.asec)
+    rng = np.random.default_rng(7)
+    g0 = (rng.standard_normal((L, R)) + 1j * rng.standard_normal((L, R))) * np.exp(-((p["r"] / p["r"][-1]) ** 2) * 3)[None, :]
+    p["g0"] = g0 / np.sqrt(np.sum(np.abs(g0) ** 2) * float(p["delta_r"]))
+    ref = cport.sh_steps(p)
+    for env in ({}, {"ION_NO_LEN_FOLD": "1", "ION_NO_SLAB": "1"}, {"ION_NO_LEN_FOLD": "1", "ION_NO_SLAB": "1", "ION_NO_PDL": "1", "ION_NO_GRAPHS": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with engine.DeviceSimulation.from_problem(p) as sim:
+            sim.step(p["taus"], p["fields"])
+            g = sim.read_g()[0]
+        for k in env:
+            monkeypatch.delenv(k)
+        assert rel_err(g, ref) < TOL, env
+
+
+def test_segmented_line_crank_nicolson_ensemble_spans_several_waves():
+    """LineMesh CN, 2^14 points (11 segments) x 48 members = 528 CTAs: every member must equal its single-member run"""
+    from ionization_b200 import engine
+
+    base = dict(load_golden("line_len_cn_1024"))
+    Z = 2 ** 14
+    z = np.linspace(-1, 1, Z) * base["z"][-1] * (Z // 1024)
+    dz = z[1] - z[0]
+    scale = (float(base["delta_z"]) / dz) ** 2
+    p = dict(base)
+    p.update(Z=Z, z=z, delta_z=dz, h_off=np.full(Z - 1, base["h_off"][0] * scale), w_z=z * (base["w_z"][-1] / base["z"][-1]), mask=np.ones(Z))
+    p["h_diag"] = np.full(Z, -2 * p["h_off"][0]) + 0j + np.interp(z, base["z"], np.real(base["h_diag"]) + 2 * base["h_off"][0])
+    rng = np.random.default_rng(3)
+    g0 = (rng.standard_normal(Z) + 1j * rng.standard_normal(Z)) * np.exp(-((z / z[-1]) ** 2) * 2)
+    p["g0"] = g0 / np.sqrt(np.sum(np.abs(g0) ** 2) * dz)
+    p["state_rows"] = p["g0"][None, :]
+    n = 12
+    members = 48
+    fields = 0.05 * np.outer(base["fields"][:n], np.linspace(0.2, 1.5, members))
+    with engine.DeviceSimulation.from_problem(p, batch=members) as sim:
+        sim.step(p["taus"][:n], fields)
+        g = sim.read_g()[:, 0]
+    for b in (0, 17, members - 1):
+        with engine.DeviceSimulation.from_problem(p) as sim:
+            sim.step(p["taus"][:n], np.ascontiguousarray(fields[:, b]))
+            g1 = sim.read_g()[0, 0]
+        assert rel_err(g[b], g1) < 1e-13

@@ -25,6 +25,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--gauge", default="LEN")
     ap.add_argument("--no-compare", action="store_true")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="peer: the engine's own halo kernel over NVLink peer memory inside the device-resident loop; "
+                         "nccl: send/recv between phases driven from Python (the baseline)")
     args = ap.parse_args()
 
     import torch
@@ -49,10 +52,20 @@ def main():
     p["g0"] = g0 / np.sqrt(np.sum(np.abs(g0) ** 2) * float(p["delta_r"]))
 
     shard = parallel.ShardedSimulation(p, rank, world, device=local)
-    ex = shard.make_exchanger()
+    peer = args.transport == "peer"
+    ex = None if peer else shard.make_exchanger()
+    if peer:
+        shard.attach_peers()
+
+    def advance(taus, fields):
+        if peer:
+            shard.step_device(taus, fields)
+        else:
+            shard.step(taus, fields, ex)
+
     what = nat.OBS_NORM | nat.OBS_INNER_PRODUCTS
-    # warm-up step (NCCL communicators, LU factors), then restore the initial state
-    shard.step(p["taus"][:1], p["fields"][:1], ex)
+    # warm-up (NCCL communicators / graph capture, LU factors), then restore the initial state
+    advance(p["taus"], p["fields"]) if peer else advance(p["taus"][:1], p["fields"][:1])
     torch.cuda.synchronize()
     shard.engine.write_g(p["g0"][shard.l_begin : shard.l_begin + shard.L].reshape(1, shard.L, R))
     dist.barrier()
@@ -61,7 +74,7 @@ def main():
     with torch.cuda.stream(shard.stream):
         e0.record()
     t0 = time.perf_counter()
-    shard.step(p["taus"], p["fields"], ex)
+    advance(p["taus"], p["fields"])
     with torch.cuda.stream(shard.stream):
         e1.record()
     e1.synchronize()
@@ -71,16 +84,33 @@ def main():
     rec = parallel.all_reduce_observation(shard.partial_observation(what, ex), device=local)
     g_mine = shard.read_g()
 
-    out = {"world": world, "r_points": R, "l_bound": L, "gauge": args.gauge, "steps": args.steps, "ms_per_step": float(ms[0]) / args.steps,
+    out = {"transport": args.transport, "world": world, "r_points": R, "l_bound": L, "gauge": args.gauge, "steps": args.steps, "ms_per_step": float(ms[0]) / args.steps,
            "updates_per_s": args.steps * R * L / (float(ms[0]) * 1e-3), "norm": float(rec[0]), "halo_bytes_per_exchange_per_neighbour": shard.R * 16,
            "exchanges_per_step": len(shard.halo_phases), "wall_s": wall}
     if not args.no_compare:
         gathered = parallel.gather_objects((shard.l_begin, g_mine))
         if rank == 0:
-            with engine.DeviceSimulation.from_problem(p, device=local) as sim:
-                sim.step(p["taus"], p["fields"])
-                g_ref = sim.read_g()[0]
-                rec_ref = sim.observe(what)[0]
+            env_keep = {k: os.environ.get(k) for k in ("ION_NO_LEN_FOLD", "ION_NO_SLAB")}
+            for mode in ("same_kernels", "best"):
+                # same_kernels: the unsharded run restricted to the kernel schedule the shards use (strong-scaling reference);
+                # best: the unsharded run with its single-GPU-only fusions (folded LEN step, VEL slab kernel)
+                if mode == "same_kernels":
+                    os.environ["ION_NO_LEN_FOLD"] = "1"
+                    os.environ["ION_NO_SLAB"] = "1"
+                else:
+                    for k, v in env_keep.items():
+                        os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+                with engine.DeviceSimulation.from_problem(p, device=local) as sim:
+                    sim.step(p["taus"], p["fields"])  # warm-up: factors, graph capture
+                    sim.write_g(np.asarray(p["g0"], dtype=np.complex128)[None])
+                    sim.synchronize()
+                    t1 = time.perf_counter()
+                    sim.step(p["taus"], p["fields"])
+                    sim.synchronize()
+                    out[f"unsharded_1gpu_ms_per_step_{mode}"] = 1e3 * (time.perf_counter() - t1) / args.steps
+                    g_ref = sim.read_g()[0]
+                    rec_ref = sim.observe(what)[0]
+            out["speedup_vs_1gpu_same_kernels"] = out["unsharded_1gpu_ms_per_step_same_kernels"] / out["ms_per_step"]
             g = np.concatenate([blk for _, blk in sorted(gathered, key=lambda x: x[0])], axis=0)
             out["max_rel_err_vs_unsharded"] = float(np.max(np.abs(g - g_ref)) / np.max(np.abs(g_ref)))
             out["norm_err"] = abs(float(rec[0]) - float(rec_ref[0]))
