@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- the driver-facing benchmark of the mesh time-evolution hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3_vel|c3_len|c1_len|c4_len]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3_vel|c3_len|c3_adi|c1_len|c4_len|c4_len_ensemble|c2_line_ensemble]
 
 Metric (BASELINE.json): grid-point updates/s of the SphericalHarmonicMesh CN + split-operator step, and the
 fraction of the B200 HBM roofline at 32 B per update.
@@ -64,6 +64,10 @@ def build_workload(name):
         return configs.config3("VEL"), "configs[2]: SphericalHarmonicMesh hydrogen 1s r_bound=250a0 r_points=2000 l_bound=500 velocity gauge split-operator, Sinc 200as, 2000 steps, single sim"
     if name == "c3_len":
         return configs.config3("LEN"), "SphericalHarmonicMesh r_points=2000 l_bound=500 length gauge split-operator, Sinc 200as, 2000 steps, single sim"
+    if name == "c3_adi":
+        p = dict(configs.config3("LEN"))
+        p["kind"] = "sh_len_adi"  # same mesh, pulse and field samples (E(t + dt/2), mesh_operators.py:1011-1013); evolution_methods.py:46-77
+        return p, "SphericalHarmonicMesh r_points=2000 l_bound=500 length gauge AlternatingDirectionImplicit, Sinc 200as, 2000 steps, single sim"
     if name == "c1_len":
         return configs.config1("LEN"), "configs[0]: SphericalHarmonicMesh r_points=500 l_bound=50 length gauge split-operator, 2000 steps"
     if name == "c4_len":
@@ -333,7 +337,7 @@ def main():
             alg_bytes = BYTES_PER_UPDATE * L * R * batch * steps_per_launch
             achieved = alg_bytes / (dom_ms / dom_n * 1e-3) / 1e9
             roofline = {
-                "bound": "hbm", "kernel": "k_resident" if dom == "resident" else ("k_slab" if dom == "slab" else f"k_unit<{dom}>"), "time_steps_per_launch": steps_per_launch, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "bound": "hbm", "kernel": {"resident": "k_resident", "slab": "k_slab", "adi_l": "k_adi_l"}.get(dom, f"k_unit<{dom}>"), "time_steps_per_launch": steps_per_launch, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "avg_launch_us": 1e3 * dom_ms / dom_n, "share_of_step": dom_ms / total_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "kernels_us": {k: round(1e3 * v[0] / v[1], 3) for k, v in prof.items()},
@@ -348,7 +352,7 @@ def main():
     d2h = batch * L * R * 16 + batch * 8 * (1 + 2 * n_states)
 
     cpu_baseline = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline and str(problem["kind"]) != "sh_len_adi":  # the C port has no ADI
         try:
             v, n_cpu, dt_cpu, cores = cpu_reference_rate(problem, seconds_target=12.0)
             cpu_baseline = {"value": v, "unit": "updates/s", "cores": cores, "kind": "port",

@@ -10,7 +10,7 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(_HERE, "csrc", "engine.cu")]
-DEPS = SRC + [os.path.join(_HERE, "csrc", n) for n in ("kernels.cuh", "common.cuh", "resident.cuh", "slab.cuh")] + [
+DEPS = SRC + [os.path.join(_HERE, "csrc", n) for n in sorted(os.listdir(os.path.join(_HERE, "csrc"))) if n.endswith(".cuh")] + [
     os.path.join(os.path.dirname(_HERE), "include", "ionization_b200.h")
 ]
 OUT = os.path.join(_HERE, "_lib", "libionization_b200.so")

@@ -1,0 +1,221 @@
+// ionization_b200 -- SphericalHarmonicMesh length gauge, AlternatingDirectionImplicit (ION_SH_LEN_ADI).
+//
+// Reference: evolution_methods.py:49-77 with total_hamiltonian = [H0 (r-wrapped), H_int (l-wrapped)]
+// (mesh_operators.py:1020-1035), i.e. per time step
+//
+//      g <- mask * (1 + i tau H0)^-1_r  (1 - i tau H_int)_l  (1 + i tau H_int)^-1_l  (1 - i tau H0)_r  g
+//
+// H_int couples channels l <-> l+1 at radius j with  E(t) * c_l * x_j  (x_j = -q r_j), zero diagonal
+// (mesh_operators.py:988-1018): for every radial point an L x L tridiagonal system ALONG l.
+//
+// k_adi_l does the first three operators in one out-of-place pass over psi:
+//   * (1 - i tau H0)_r is applied while loading: three reads per point (own row and both r-neighbours, which sit at
+//     other positions of the row-interleaved layout and mostly hit L1/L2);
+//   * the l-solve: a CTA owns PW consecutive positions x all L channels; thread (c, q) holds the CL = 8 channels
+//     8c .. 8c+7 of position q in registers.  With s = tau E x_j and beta_l = s c_l the matrix is 1 on the diagonal and
+//     i beta_l off it, so its pivots are REAL: p_l = 1 + beta_{l-1}^2 / p_{l-1}.  w_l = 1/p_l obeys the Moebius map
+//     w -> 1 / (1 + a w); every thread composes its 8 maps into one 2x2 real matrix, the chunk inflows follow from a
+//     sequential walk over the preceding chunks' matrices in shared memory (one division per chunk), exactly.
+//     Forward / backward substitution are affine recurrences with multipliers -i beta w: zero-inflow pass, chunk
+//     aggregates to shared memory, sequential prefix over the preceding (following) chunks, second pass with the true
+//     inflow -- the same scheme as the radial Crank-Nicolson scans (kernels.cuh), across chunks instead of lanes;
+//   * (1 - i tau H_int)(1 + i tau H_int)^-1 v = 2 (1 + i tau H_int)^-1 v - v: no second mat-vec.
+// The remaining (1 + i tau H0)^-1_r and the mask are k_unit<PROG_CN> with F_SOLVE_ONLY | F_MASK.
+// PW = 8 positions are one full 128-byte line per channel; L <= 8 * 512 channels.
+#pragma once
+#include "common.cuh"
+
+namespace ion {
+
+struct AdiParams {
+    const cplx *psi;         // [batch][L][M][T]
+    cplx *out;               // same shape, a different buffer
+    const cplx *thd;         // [L][M][T]  tau * h_diag, permuted (k_make_thd)
+    const double *toff;      // [M][T]     tau * h_off[i] (0 for i >= R-1)
+    const double *toff_prev; // [T]        tau * h_off[t*M - 1] (0 for t = 0)
+    const double *vec;       // [M][T]     x_j, 0 in the padding
+    const double *cl;        // [L-1]      c_l
+    const double *scal;      // [batch]    tau * E of this step
+    int L, T, M, PW, NC;
+};
+
+constexpr int ADI_CL = 8;
+constexpr int ADI_MAX_THREADS = 512;
+
+// (-i e) v for real e
+ION_DEVINL cplx mul_mi(double e, cplx v) { return c_make(e * v.y, -e * v.x); }
+// (-i e) v + a
+ION_DEVINL cplx fma_mi(double e, cplx v, cplx a) { return c_make(fma(e, v.y, a.x), fma(-e, v.x, a.y)); }
+
+__global__ void __launch_bounds__(ADI_MAX_THREADS, 1) k_adi_l(const AdiParams p)
+{
+    constexpr int CL = ADI_CL;
+    __shared__ double sm[4 * ADI_MAX_THREADS];
+    const int NT = blockDim.x, tid = threadIdx.x;
+    const int q = tid % p.PW, c = tid / p.PW;
+    const int T = p.T, M = p.M, L = p.L;
+    const size_t Rp = (size_t)M * T;
+    const int pos = blockIdx.x * p.PW + q;
+    const int b = blockIdx.y;
+    const int l0 = c * CL;
+    pdl_launch_dependents();
+
+    // r-neighbours of row i = t*M + k in the interleaved layout
+    const int k_row = pos / T, t = pos % T;
+    double t_hi = p.toff[pos], t_lo;
+    int pos_lo, pos_hi;
+    if (k_row > 0) {
+        pos_lo = pos - T;
+        t_lo = p.toff[pos_lo];
+    } else if (t > 0) {
+        pos_lo = (M - 1) * T + t - 1;
+        t_lo = p.toff_prev[t];
+    } else {
+        pos_lo = pos;
+        t_lo = 0.0;
+    }
+    if (k_row < M - 1) {
+        pos_hi = pos + T;
+    } else if (t + 1 < T) {
+        pos_hi = t + 1;
+    } else {
+        pos_hi = pos;
+        t_hi = 0.0;
+    }
+    const double s = p.scal[b] * p.vec[pos];
+    // bq[k]: coupling of channel l0+k with the channel below it; bq[CL]: of the chunk's last channel with the next chunk
+    double bq[CL + 1];
+#pragma unroll
+    for (int k = 0; k <= CL; ++k) {
+        const int l = l0 + k;
+        bq[k] = (l >= 1 && l < L) ? s * p.cl[l - 1] : 0.0;
+    }
+    // Moebius chunk matrix of w -> 1 / (1 + a w):  [[0, 1], [a, 1]] per channel, later channels on the left
+    {
+        double A = 1.0, B = 0.0, C = 0.0, D = 1.0;
+#pragma unroll
+        for (int k = 0; k < CL; ++k) {
+            if (l0 + k < L) {
+                const double a = bq[k] * bq[k];
+                const double nA = C, nB = D;
+                C = fma(a, A, C);
+                D = fma(a, B, D);
+                A = nA;
+                B = nB;
+            }
+        }
+        sm[0 * NT + tid] = A;
+        sm[1 * NT + tid] = B;
+        sm[2 * NT + tid] = C;
+        sm[3 * NT + tid] = D;
+    }
+    __syncthreads();
+    double w_in = 1.0;  // irrelevant for chunk 0 (its first coupling is zero)
+    for (int kk = 0; kk < c; ++kk) {
+        const int j = kk * p.PW + q;
+        const double A = sm[0 * NT + j], B = sm[1 * NT + j], C = sm[2 * NT + j], D = sm[3 * NT + j];
+        w_in = fma(A, w_in, B) / fma(C, w_in, D);
+    }
+    __syncthreads();
+    double w[CL];
+    {
+        double wp = w_in;
+#pragma unroll
+        for (int k = 0; k < CL; ++k) {
+            if (l0 + k < L) wp = 1.0 / fma(bq[k] * bq[k], wp, 1.0);
+            else wp = 1.0;
+            w[k] = wp;
+        }
+    }
+
+    // ---- load, (1 - i tau H0)_r on the fly ------------------------------------------------------
+    pdl_wait();
+    cplx g1[CL];
+#pragma unroll
+    for (int k = 0; k < CL; ++k) {
+        const int l = l0 + k;
+        g1[k] = c_zero();
+        if (l < L) {
+            const cplx *ch = p.psi + ((size_t)b * L + l) * Rp;
+            const cplx g = ch[pos], glo = ch[pos_lo], ghi = ch[pos_hi];
+            const cplx d = p.thd[(size_t)l * Rp + pos];
+            cplx z = c_mul(d, g);
+            z = c_make(fma(t_lo, glo.x, z.x), fma(t_lo, glo.y, z.y));
+            z = c_make(fma(t_hi, ghi.x, z.x), fma(t_hi, ghi.y, z.y));
+            g1[k] = c_make(g.x + z.y, g.y - z.x);  // g - i z
+        }
+    }
+
+    // ---- forward substitution: y_l = g_l - i (beta_{l-1} w_{l-1}) y_{l-1} --------------------------
+    double ef[CL];  // beta_{l-1} w_{l-1}
+    ef[0] = bq[0] * w_in;
+#pragma unroll
+    for (int k = 1; k < CL; ++k) ef[k] = bq[k] * w[k - 1];
+    {
+        cplx z = g1[0], m = c_make(0.0, -ef[0]);
+#pragma unroll
+        for (int k = 1; k < CL; ++k) {
+            z = fma_mi(ef[k], z, g1[k]);
+            m = mul_mi(ef[k], m);
+        }
+        sm[0 * NT + tid] = m.x;
+        sm[1 * NT + tid] = m.y;
+        sm[2 * NT + tid] = z.x;
+        sm[3 * NT + tid] = z.y;
+    }
+    __syncthreads();
+    cplx yin = c_zero();
+    for (int kk = 0; kk < c; ++kk) {
+        const int j = kk * p.PW + q;
+        yin = c_fma(c_make(sm[0 * NT + j], sm[1 * NT + j]), yin, c_make(sm[2 * NT + j], sm[3 * NT + j]));
+    }
+    __syncthreads();
+    cplx y[CL];
+    y[0] = fma_mi(ef[0], yin, g1[0]);
+#pragma unroll
+    for (int k = 1; k < CL; ++k) y[k] = fma_mi(ef[k], y[k - 1], g1[k]);
+
+    // ---- backward substitution: x_l = w_l y_l - i (beta_l w_l) x_{l+1} -----------------------------
+    double eb[CL];
+#pragma unroll
+    for (int k = 0; k < CL; ++k) eb[k] = bq[k + 1] * w[k];
+    {
+        cplx z = c_scale(y[CL - 1], w[CL - 1]), m = c_make(0.0, -eb[CL - 1]);
+#pragma unroll
+        for (int k = CL - 2; k >= 0; --k) {
+            z = fma_mi(eb[k], z, c_scale(y[k], w[k]));
+            m = mul_mi(eb[k], m);
+        }
+        sm[0 * NT + tid] = m.x;
+        sm[1 * NT + tid] = m.y;
+        sm[2 * NT + tid] = z.x;
+        sm[3 * NT + tid] = z.y;
+    }
+    __syncthreads();
+    cplx xin = c_zero();
+    for (int kk = p.NC - 1; kk > c; --kk) {
+        const int j = kk * p.PW + q;
+        xin = c_fma(c_make(sm[0 * NT + j], sm[1 * NT + j]), xin, c_make(sm[2 * NT + j], sm[3 * NT + j]));
+    }
+    // true inflow; out = 2 x - g1 = (1 - i tau H_int) x
+    cplx x = xin;
+#pragma unroll
+    for (int k = CL - 1; k >= 0; --k) {
+        x = fma_mi(eb[k], x, c_scale(y[k], w[k]));
+        const int l = l0 + k;
+        if (l < L) p.out[((size_t)b * L + l) * Rp + pos] = c_make(fma(2.0, x.x, -g1[k].x), fma(2.0, x.y, -g1[k].y));
+    }
+}
+
+// tau * h_diag of every channel, permuted to the interleaved layout: [L][M][T]
+__global__ void k_make_thd(const cplx *__restrict__ h_diag, double tau, int R, int M, int T, cplx *__restrict__ thd)
+{
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= M * T) return;
+    const int l = blockIdx.y;
+    const int k = pos / T, t = pos % T;
+    const long long i = (long long)t * M + k;
+    thd[(size_t)l * M * T + pos] = (i < R) ? c_scale(h_diag[(size_t)l * R + i], tau) : c_zero();
+}
+
+}  // namespace ion

@@ -26,6 +26,7 @@
 #include "kernels.cuh"
 #include "resident.cuh"
 #include "slab.cuh"
+#include "adi.cuh"
 #include "halo.cuh"
 
 namespace {
@@ -62,11 +63,13 @@ enum KernelKind : int {
     KK_SLAB,
     KK_LEN_STEP,
     KK_HALO,
+    KK_ADI_L,
     KK_COUNT
 };
 const char *const kKernelNames[KK_COUNT] = {"rot",        "rot_cn_rot", "h2",        "h2_cn_h2", "cn",     "line_so_len",
                                             "line_so_vel", "line_cn",    "sweep_flat", "mask",    "observe",
-                                            "resident",    "slab",       "len_step",   "halo"};
+                                            "resident",    "slab",       "len_step",   "halo",
+                                            "adi_l"};
 
 template <typename T>
 int dev_alloc(T **p, size_t n)
@@ -114,6 +117,7 @@ struct ion_sim {
     double *h_off = nullptr;
     std::vector<double> h_off_host;
     cplx *w = nullptr, *aggP = nullptr, *aggQ = nullptr, *th = nullptr;
+    cplx *thd = nullptr;  // [L][M][T] tau * h_diag, permuted (ION_SH_LEN_ADI: explicit r half-step, adi.cuh)
     double *toff = nullptr, *toff_prev = nullptr;
     double *vec = nullptr, *zvec = nullptr, *zprev = nullptr, *mask = nullptr, *rvec = nullptr;
     double *cl = nullptr, *cl2 = nullptr, *cl_z = nullptr;
@@ -173,6 +177,7 @@ struct ion_sim {
         if (scal_chunk) cudaFree(scal_chunk);
         if (scal_phase) cudaFree(scal_phase);
         if (th) cudaFree(th);
+        if (thd) cudaFree(thd);
         if (obs_chunk) cudaFree(obs_chunk);
         if (halo) cudaFree(halo);
         for (void *q : peer_ipc_base)
@@ -357,7 +362,8 @@ int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, c
     dim3 grid(units * s->S, s->batch);
     if (prog == ion::PROG_ROT) p.H = 0;  // point-wise in r: interior threads only
     // r-segments: a kernel that reads halo rows (every program but the point-wise rotation) must not run in place
-    const bool seg_oop = s->S > 1 && prog != ion::PROG_ROT && prog != ion::PROG_LEN_STEP;
+    // the ADI solve goes back to the buffer the l-pass read from, so that a step ends where it began
+    const bool seg_oop = (s->S > 1 && prog != ion::PROG_ROT && prog != ion::PROG_LEN_STEP) || (prog == ion::PROG_CN && (flags & ion::F_SOLVE_ONLY));
     if (seg_oop) {
         if (!s->psi2) return fail(ION_ESTATE, "internal: second wavefunction buffer missing for a segmented kernel");
         p.psi_out = s->psi2;
@@ -510,6 +516,12 @@ int ensure_factor(ion_sim *s, double tau)
             ion::k_make_th<<<(s->Rp + 127) / 128, 128, 0, s->stream>>>(s->h_diag, tau, s->R, s->M, s->T, s->th);
             CUDA_TRY(cudaGetLastError());
         }
+        if (s->program == ION_SH_LEN_ADI) {
+            if (int rc = dev_alloc(&s->thd, (size_t)s->L * s->Rp)) return rc;
+            dim3 g3((s->Rp + 127) / 128, s->L);
+            ion::k_make_thd<<<g3, 128, 0, s->stream>>>(s->h_diag, tau, s->R, s->M, s->T, s->thd);
+            CUDA_TRY(cudaGetLastError());
+        }
         if (s->S > 1) {
             // r-segments: the halo must cover the reach; programs with r-pair bricks (velocity gauge) get one more warp of
             // margin per unit of reach for the brick edge effects
@@ -629,6 +641,46 @@ int launch_slab(ion_sim *s, const double *sa, const double *sb)
     return ION_OK;
 }
 
+// ION_SH_LEN_ADI: explicit r half-step, implicit + explicit l half-steps in one out-of-place pass (adi.cuh)
+int launch_adi_l(ion_sim *s, const double *sa)
+{
+    if (!s->psi2 || !s->thd) return fail(ION_ESTATE, "internal: ADI buffers missing");
+    ion::AdiParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.psi = s->psi;
+    p.out = s->psi2;
+    p.thd = s->thd;
+    p.toff = s->toff;
+    p.toff_prev = s->toff_prev;
+    p.vec = s->vec;
+    p.cl = s->cl;
+    p.scal = sa;
+    p.L = s->L;
+    p.T = s->T;
+    p.M = s->M;
+    p.NC = (s->L + ion::ADI_CL - 1) / ion::ADI_CL;
+    int pw = 32;
+    while (pw > 1 && pw * p.NC > ion::ADI_MAX_THREADS) pw /= 2;
+    p.PW = pw;
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(s->Rp / pw, s->batch);
+    cfg.blockDim = dim3(pw * p.NC);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = s->use_pdl ? 1 : 0;
+    prof_begin(s, KK_ADI_L);
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_adi_l, p));
+    prof_end(s);
+    s->launch_count++;
+    std::swap(s->psi, s->psi2);
+    return ION_OK;
+}
+
 // bring the current state back into the buffer the rest of the API (and every captured graph) starts from
 int restore_home(ion_sim *s)
 {
@@ -719,6 +771,10 @@ int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, int pre, b
             if ((rc = launch_sweep_flat(s, 0, F_REAL_ROT, sa))) return rc;
             return launch_mask(s);
         }
+        case ION_SH_LEN_ADI:
+            // (1 - i tau H0)_r, (1 + i tau Hint)^-1_l, (1 - i tau Hint)_l | (1 + i tau H0)^-1_r, mask   (evolution_methods.py:49-77)
+            if ((rc = launch_adi_l(s, sa))) return rc;
+            return launch_unit(s, PROG_CN, 0, F_MASK | F_SOLVE_ONLY, nullptr, nullptr);
         case ION_LINE_LEN_SO: return launch_unit(s, PROG_LINE_SO_LEN, 0, F_MASK, sa, nullptr);
         case ION_LINE_VEL_SO: return launch_unit(s, PROG_LINE_SO_VEL, 0, F_MASK, sa, nullptr);
         case ION_LINE_LEN_CN: return launch_unit(s, PROG_LINE_CN, 0, F_MASK, sa, nullptr);
@@ -970,7 +1026,7 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
     if (int rc = resident_prepare(s)) return rc;
     if (int rc = slab_prepare(s)) return rc;
     if (int rc = len_fold_prepare(s)) return rc;
-    if (s->S > 1)
+    if (s->S > 1 || s->program == ION_SH_LEN_ADI)
         if (int rc = ensure_second_buffer(s)) return rc;  // segmented kernels run out of place
     if (s->resident_state == 1 && uniform_tau) {
         // on-chip resident kernel: one persistent launch per stretch between observations
@@ -1156,7 +1212,8 @@ int ion_sim_create_sharded(int program, int64_t L_total, int64_t l_begin, int64_
     const bool line = (program == ION_LINE_LEN_CN || program == ION_LINE_LEN_SO || program == ION_LINE_VEL_SO);
     if (program < 0 || program > ION_SH_LEN_ADI) return fail(ION_EINVAL, "unknown program");
     if (line && L_total != 1) return fail(ION_EINVAL, "LineMesh programs need L = 1");
-    if (program == ION_SH_LEN_ADI) return fail(ION_ENOTSUP, "ION_SH_LEN_ADI is not implemented in this build");
+    if (program == ION_SH_LEN_ADI && L_total > ion::ADI_CL * ion::ADI_MAX_THREADS)
+        return fail(ION_ENOTSUP, "ION_SH_LEN_ADI: at most 4096 channels (one CTA holds all channels of a radial position)");
     const bool sharded = (L != L_total);
     if (sharded) {
         if (batch != 1) return fail(ION_ENOTSUP, "l-block shards hold one simulation (batch = 1)");
@@ -1170,7 +1227,7 @@ int ion_sim_create_sharded(int program, int64_t L_total, int64_t l_begin, int64_
     int M = 4;
     if (const char *env = std::getenv("ION_M"))
     {
-        if (env[0] == '8' && R <= 2048) M = 8;              // experiment: 256 threads x 8 rows
+        if (env[0] == '8' && R <= 2048 && program != ION_SH_LEN_ADI) M = 8;              // experiment: 256 threads x 8 rows
     }
     int64_t T = (R + M - 1) / M;
     T = (T + 31) / 32 * 32;
@@ -1272,7 +1329,7 @@ int ion_sim_set_len_coupling(ion_sim_t *s, const double *c_l, const double *x_j)
 {
     if (!s || !x_j || (s->L_total > 1 && !c_l)) return fail(ION_EINVAL, "NULL argument");
     s->invalidate_graphs();
-    if (s->program != ION_SH_LEN_SO) return fail(ION_EINVAL, "length-gauge coupling does not belong to this program");
+    if (s->program != ION_SH_LEN_SO && s->program != ION_SH_LEN_ADI) return fail(ION_EINVAL, "length-gauge coupling does not belong to this program");
     CUDA_TRY(cudaSetDevice(s->device));
     if (int rc = upload_plain(s, c_l, (size_t)s->L_total - 1, &s->cl)) return rc;
     if (int rc = upload_plain(s, c_l, (size_t)s->L_total - 1, &s->cl_z)) return rc;
@@ -1562,7 +1619,7 @@ int ion_sim_prepare(ion_sim_t *s, double tau)
     CUDA_TRY(cudaSetDevice(s->device));
     if (int rc = check_ready(s)) return rc;
     if (int rc = ensure_factor(s, tau)) return rc;
-    if (s->S > 1)
+    if (s->S > 1 || s->program == ION_SH_LEN_ADI)
         if (int rc = ensure_second_buffer(s)) return rc;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return ION_OK;
@@ -1644,7 +1701,7 @@ int ion_sim_step_phase(ion_sim_t *s, int phase, double tau, const double *field)
         CUDA_TRY(cudaMemcpyAsync(s->scal_phase, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
     }
-    if (s->S > 1)
+    if (s->S > 1 || s->program == ION_SH_LEN_ADI)
         if (int rc = ensure_second_buffer(s)) return rc;
     if (int rc = launch_unit(s, ph[phase].prog, ph[phase].parity, ph[phase].flags, s->scal_phase, nullptr)) return rc;
     return restore_home(s);  // the caller's halo buffers point into the home buffer

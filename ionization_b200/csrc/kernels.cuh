@@ -23,6 +23,7 @@ enum : int {
     F_MASK = 1,       // multiply by mask[r] at the end (mesh/meshes.py:257)
     F_REAL_ROT = 2,   // rotation [[c, s], [-s, c]] (velocity gauge h1 / line) instead of [[c, -is], [-is, c]]
     F_H2_REVERSE = 4, // r-sublayer order: default (r-even, r-odd); reversed (r-odd, r-even)
+    F_SOLVE_ONLY = 8, // PROG_CN: (1 + i tau H0)^-1 g instead of the Crank-Nicolson (1 + i tau H0)^-1 (1 - i tau H0) g  (ADI, adi.cuh)
 };
 
 struct UnitParams {
@@ -811,7 +812,14 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
             h2_pair<M>(A, B, ang, true, tl, Tc, xs);  // (oo, oe)
         }
     } else if (PROG == PROG_CN) {
+        cplx A0[M];
+#pragma unroll
+        for (int k = 0; k < M; ++k) A0[k] = A[k];
         cn_channel<M>(A, fA, toff, toff_prev, tl, Tc, sm_scan, short_scan);
+        if (p.flags & F_SOLVE_ONLY) {  // cn_channel returns 2x - g with x = (1 + i tau H0)^-1 g
+#pragma unroll
+            for (int k = 0; k < M; ++k) A[k] = c_make(0.5 * (A[k].x + A0[k].x), 0.5 * (A[k].y + A0[k].y));
+        }
         if (p.flags & F_MASK) {
             double mk[M];
             load_vec<M>(mk, p.mask, T, t, ok);

@@ -168,3 +168,105 @@ def run_sh_model(p, M=4, fused=True):
     else:
         raise ValueError(kind)
     return g[:, :R]
+
+
+# ---------------------------------------------------------------------------------------------
+# ION_SH_LEN_ADI (csrc/adi.cuh): per radial position an L x L tridiagonal solve along l, cut into chunks of CL channels
+# ---------------------------------------------------------------------------------------------
+def adi_l_pass(g1, beta, CL=8):
+    """g1: (L,) right-hand side at one radial position; beta: (L-1,) real couplings (tau E c_l x_j).
+    Returns (1 - i B)(1 + i B)^-1 g1 the way k_adi_l computes it: real pivots through composed Moebius maps,
+    chunked affine recurrences with sequential prefixes over the chunk aggregates, 2x - g1 at the end."""
+    L = len(g1)
+    NC = -(-L // CL)
+    bq = np.zeros(NC * CL + 1)  # bq[l]: coupling of channel l with l-1
+    bq[1:L] = beta
+    # chunk matrices of w -> 1 / (1 + a w)
+    mats = []
+    for c in range(NC):
+        A, B, C, D = 1.0, 0.0, 0.0, 1.0
+        for l in range(c * CL, min(L, (c + 1) * CL)):
+            a = bq[l] ** 2
+            A, B, C, D = C, D, a * A + C, a * B + D
+        mats.append((A, B, C, D))
+    w = np.ones(NC * CL)
+    w_in = np.ones(NC)
+    for c in range(NC):
+        wi = 1.0
+        for kk in range(c):
+            A, B, C, D = mats[kk]
+            wi = (A * wi + B) / (C * wi + D)
+        w_in[c] = wi
+        wp = wi
+        for l in range(c * CL, min(L, (c + 1) * CL)):
+            wp = 1.0 / (bq[l] ** 2 * wp + 1.0)
+            w[l] = wp
+    gp = np.zeros(NC * CL, dtype=np.complex128)
+    gp[:L] = g1
+    ef = np.zeros(NC * CL)
+    for c in range(NC):
+        ef[c * CL] = bq[c * CL] * w_in[c]
+        for k in range(1, CL):
+            ef[c * CL + k] = bq[c * CL + k] * w[c * CL + k - 1]
+    # forward
+    Mc, Yc = [], []
+    for c in range(NC):
+        z, m = gp[c * CL], -1j * ef[c * CL]
+        for k in range(1, CL):
+            z = gp[c * CL + k] - 1j * ef[c * CL + k] * z
+            m = -1j * ef[c * CL + k] * m
+        Mc.append(m)
+        Yc.append(z)
+    y = np.zeros(NC * CL, dtype=np.complex128)
+    for c in range(NC):
+        yin = 0
+        for kk in range(c):
+            yin = Mc[kk] * yin + Yc[kk]
+        prev = yin
+        for k in range(CL):
+            prev = gp[c * CL + k] - 1j * ef[c * CL + k] * prev
+            y[c * CL + k] = prev
+    # backward
+    eb = bq[1:] * w
+    Qc, Xc = [], []
+    for c in range(NC):
+        hi = c * CL + CL - 1
+        z, m = w[hi] * y[hi], -1j * eb[hi]
+        for l in range(hi - 1, c * CL - 1, -1):
+            z = w[l] * y[l] - 1j * eb[l] * z
+            m = -1j * eb[l] * m
+        Qc.append(m)
+        Xc.append(z)
+    out = np.zeros(NC * CL, dtype=np.complex128)
+    for c in range(NC):
+        xin = 0
+        for kk in range(NC - 1, c, -1):
+            xin = Qc[kk] * xin + Xc[kk]
+        x = xin
+        for l in range(c * CL + CL - 1, c * CL - 1, -1):
+            x = w[l] * y[l] - 1j * eb[l] * x
+            out[l] = 2 * x - gp[l]
+    return out[:L]
+
+
+def run_sh_adi_model(p, CL=8):
+    """engine schedule of ION_SH_LEN_ADI: [explicit r + l pass] then [(1 + i tau H0)^-1 = (CN + 1)/2, mask]."""
+    L, R = int(p["L"]), int(p["R"])
+    g = np.array(p["g0"], dtype=np.complex128)
+    hd, ho = np.asarray(p["h_diag"]), np.asarray(p["h_off"])
+    c_l, x_j, mask = np.asarray(p["c_l"]), np.asarray(p["x_j"]), np.asarray(p["mask"])
+    M = 4
+    T = -(-(-(-R // M)) // 32) * 32
+    for tau, E in zip(p["taus"], p["fields"]):
+        g1 = (1 - 1j * tau * hd) * g
+        g1[:, 1:] += (-1j * tau * ho) * g[:, :-1]
+        g1[:, :-1] += (-1j * tau * ho) * g[:, 1:]
+        g2 = np.empty_like(g1)
+        for j in range(R):
+            g2[:, j] = adi_l_pass(g1[:, j], tau * E * c_l * x_j[j], CL)
+        w, e, P, Q = factor(hd, ho, tau, M, T)
+        for l in range(L):
+            row = _pad(g2[l][None, :], M * T)[0]
+            g2[l] = (0.5 * (cn_channel(row, w[l], e[l], P[l], Q[l], M, T) + row))[:R]
+        g = g2 * mask[None, :]
+    return g

@@ -12,3 +12,13 @@ from engine_model import run_sh_model
 def test_engine_algorithm_matches_reference(name, fused, M):
     p = load_golden(name)
     assert rel_err(run_sh_model(p, M=M, fused=fused), p["g_final"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["sh_len_adi_64x8", "sh_len_adi_65x9"])
+@pytest.mark.parametrize("CL", [2, 8])
+def test_adi_l_pass_algorithm_matches_reference(name, CL):
+    """ION_SH_LEN_ADI (csrc/adi.cuh): real pivots through composed Moebius maps + chunked affine recurrences."""
+    from engine_model import run_sh_adi_model
+
+    p = load_golden(name)
+    assert rel_err(run_sh_adi_model(p, CL=CL), p["g_final"]) < 1e-12

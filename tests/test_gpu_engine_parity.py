@@ -24,6 +24,8 @@ SH_SMALL = [
     "sh_vel_so_61x8",
     "sh_len_so_datastores_120x12",
     "sh_vel_so_datastores_120x12",
+    "sh_len_adi_64x8",
+    "sh_len_adi_65x9",
 ]
 
 
@@ -143,13 +145,14 @@ def test_config1_full_pulse(name):
     assert abs(ion_gpu - ion_ref) <= TOL * abs(ion_ref)
 
 
-@pytest.mark.parametrize("name", ["known_sh_len_so_500x200", "known_sh_vel_so_500x200"])
+@pytest.mark.parametrize("name", ["known_sh_len_so_500x200", "known_sh_vel_so_500x200", "known_sh_len_adi_500x200"])
 def test_known_answers_of_the_reference(name):
-    """dev/meshes/mesh_refactoring_helper.py:204-251: final initial-state overlaps 0.312928752359 (LEN SO) and
-    0.319513371899 (VEL SO), numeric eigenstates, 800 steps."""
+    """dev/meshes/mesh_refactoring_helper.py:204-251: final initial-state overlaps 0.312928752359 (LEN SO),
+    0.319513371899 (VEL SO) and 0.312910470190 (LEN ADI), numeric eigenstates, 800 steps."""
     eng = _engine()
     p = load_golden(name)
-    expected = {"known_sh_len_so_500x200": 0.312928752359, "known_sh_vel_so_500x200": 0.319513371899}[name]
+    expected = {"known_sh_len_so_500x200": 0.312928752359, "known_sh_vel_so_500x200": 0.319513371899,
+                "known_sh_len_adi_500x200": 0.312910470190}[name]
     what = eng.nat.OBS_NORM | eng.nat.OBS_INNER_PRODUCTS
     with eng.DeviceSimulation.from_problem(p) as sim:
         sim.step(p["taus"], p["fields"])
@@ -398,3 +401,47 @@ def test_length_gauge_folded_step_with_sparse_observations_and_ensemble():
             assert np.max(np.abs(rec[:, b, :] - rec_b[:, 0, :])) < 1e-13
     finally:
         del os.environ["ION_NO_LEN_FOLD"]
+
+
+def test_adi_ensemble_with_different_fields_and_sparse_observations():
+    """ION_SH_LEN_ADI (evolution_methods.py:49-77) as a batch: every member has its own field series; observations every 7th
+    step go through the CUDA-graph chunks.  Checked against the oracle member by member."""
+    from oracle import restate
+
+    eng = _engine()
+    p = load_golden("sh_len_adi_64x8")
+    n, batch = len(p["taus"]), 3
+    scale = np.array([1.0, -0.5, 2.5])
+    fields = p["fields"][:, None] * scale[None, :]
+    mask = np.zeros(n, dtype=np.uint8)
+    mask[6::7] = 1
+    with eng.DeviceSimulation.from_problem(p, batch=batch) as sim:
+        rec = sim.run(p["taus"], fields, mask, eng.nat.OBS_NORM)
+        g = sim.read_g()
+    for b in range(batch):
+        q = dict(p)
+        q["fields"] = fields[:, b]
+        ref = restate.run_sh(q, store_every_step=True)
+        assert rel_err(g[b], ref["g"]) < TOL
+        assert np.max(np.abs(rec[:, b, 0] - ref["norm"][1:][mask.astype(bool)])) < TOL
+
+
+@pytest.mark.parametrize("L,R", [(70, 150), (513, 40), (9, 4100)])
+def test_adi_chunk_geometries_against_oracle(L, R):
+    """l-pass thread geometries: several chunks per position with PW = 32 / 4 positions per CTA, and an r-segmented mesh."""
+    from ionization_b200 import configs, units as u
+    from oracle import restate
+
+    eng = _engine()
+    p = configs.spherical_harmonic_problem(r_bound=0.1 * R * u.bohr_radius, r_points=R, l_bound=L, gauge="LEN", n_steps=12)
+    p["kind"] = "sh_len_adi"
+    rng = np.random.default_rng(0)
+    g0 = np.array(p["g0"])
+    g0 = g0 + 0.05 * (rng.standard_normal(g0.shape) + 1j * rng.standard_normal(g0.shape)) * np.exp(-np.arange(L)[:, None] / 20.0)
+    p["g0"] = g0 / np.sqrt(restate.norm(g0, float(p["delta_r"])))
+    p["fields"] = np.asarray(p["fields"]) * 30.0 + 1e10  # strong coupling across many channels
+    with eng.DeviceSimulation.from_problem(p, with_states=False) as sim:
+        sim.step(p["taus"], p["fields"])
+        g = sim.read_g()[0]
+    ref = restate.run_sh(p, store_every_step=False)
+    assert rel_err(g, ref["g"]) < TOL

@@ -170,3 +170,21 @@ def test_ensemble_equals_individual_runs():
         assert rel_err(s.mesh.g, single.mesh.g) < 1e-13
         assert np.max(np.abs(s.data.norm - single.data.norm)) < 1e-13
         assert np.max(np.abs(_ips(s) - _ips(single))) < 1e-13
+
+
+def test_spherical_harmonic_adi_through_the_api():
+    """SphericalHarmonicLengthGaugeOperators + AlternatingDirectionImplicit (evolution_methods.py:46-77):
+    the spec of the reference fixture sh_len_adi_64x8 (oracle/make_golden.py: small_sh_kwargs(64, 8, 40, 20))."""
+    ref = load_golden("sh_len_adi_64x8")
+    rb = 30 * u.bohr_radius
+    spec = c1_spec(
+        "LEN", r_bound=rb, r_points=64, l_bound=8, time_initial=-20 * u.asec, time_final=20 * u.asec,
+        electric_potential=P.SincPulse(pulse_width=20 * u.asec, fluence=1 * u.Jcm2, phase=0),
+        mask=P.RadialCosineMask(inner_radius=0.8 * rb, outer_radius=rb, smoothness=8),
+        evolution_method=ion.mesh.AlternatingDirectionImplicit(), store_data_every=1,
+    )
+    sim = spec.to_sim()
+    sim.run()
+    assert np.max(np.abs(sim.data.norm - ref["norm"])) < TOL
+    assert np.max(np.abs(_ips(sim) - ref["inner_products"])) < TOL
+    assert rel_err(sim.mesh.g, ref["g_final"]) < TOL
