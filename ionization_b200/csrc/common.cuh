@@ -111,12 +111,11 @@ ION_DEVINL void sincos_reduced(double theta, double *sn, double *cs)
 
 // cos/sin of N angles of one thread.  The path is chosen per WARP (a vote over the converged lanes), so the N
 // evaluations of a path are straight-line code the scheduler can interleave, and warps never diverge here.
+// `amax`: an upper bound of |theta[k]| known to the caller (e.g. |kappa| * max|v_j| for theta_j = kappa * v_j, which
+// rounds monotonically), so that the selection costs one multiplication instead of N compares.
 template <int N>
-ION_DEVINL void fast_sincos_n(const double (&theta)[N], double (&sn)[N], double (&cs)[N])
+ION_DEVINL void fast_sincos_n_bounded(const double (&theta)[N], double (&sn)[N], double (&cs)[N], double amax)
 {
-    double amax = fabs(theta[0]);
-#pragma unroll
-    for (int k = 1; k < N; ++k) amax = fmax(amax, fabs(theta[k]));
     const unsigned lanes = __activemask();
     if (__all_sync(lanes, amax <= 0.0625)) {
 #pragma unroll
@@ -135,6 +134,14 @@ ION_DEVINL void fast_sincos_n(const double (&theta)[N], double (&sn)[N], double 
             cs[k] = r.y;
         }
     }
+}
+template <int N>
+ION_DEVINL void fast_sincos_n(const double (&theta)[N], double (&sn)[N], double (&cs)[N])
+{
+    double amax = fabs(theta[0]);
+#pragma unroll
+    for (int k = 1; k < N; ++k) amax = fmax(amax, fabs(theta[k]));
+    fast_sincos_n_bounded<N>(theta, sn, cs, amax);
 }
 
 // Programmatic dependent launch (PDL).  Every kernel of a time step depends on the wavefunction written by the

@@ -416,15 +416,26 @@ ION_DEVINL void rpair_layer_odd(cplx (&S)[M], cplx (&D)[M], const RPairAngles<M>
     }
 }
 
+// Hadamard over the l-pair without its 1/sqrt(2) on the way in (the bricks are linear) ...
 template <int M>
-ION_DEVINL void hadamard(cplx (&A)[M], cplx (&B)[M])
+ION_DEVINL void hadamard_in(cplx (&A)[M], cplx (&B)[M])
 {
-    const double rs2 = 0.70710678118654752440;
 #pragma unroll
     for (int k = 0; k < M; ++k) {
         cplx a = A[k], b = B[k];
-        A[k] = c_make((a.x + b.x) * rs2, (a.y + b.y) * rs2);
-        B[k] = c_make((a.x - b.x) * rs2, (a.y - b.y) * rs2);
+        A[k] = c_add(a, b);  // sqrt(2) S
+        B[k] = c_sub(a, b);  // sqrt(2) D
+    }
+}
+// ... and both factors (1/2, exact) on the way out: 3 instructions per component pair
+template <int M>
+ION_DEVINL void hadamard_out(cplx (&A)[M], cplx (&B)[M])
+{
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        const cplx h = c_scale(A[k], 0.5), d = B[k];
+        A[k] = c_make(fma(0.5, d.x, h.x), fma(0.5, d.y, h.y));
+        B[k] = c_make(fma(-0.5, d.x, h.x), fma(-0.5, d.y, h.y));
     }
 }
 
@@ -432,7 +443,7 @@ ION_DEVINL void hadamard(cplx (&A)[M], cplx (&B)[M])
 template <int M>
 ION_DEVINL void h2_pair(cplx (&A)[M], cplx (&B)[M], const RPairAngles<M> &ang, bool reverse, int t, int T, cplx *xs)
 {
-    hadamard<M>(A, B);
+    hadamard_in<M>(A, B);
     if (!reverse) {
         rpair_layer_even<M, true>(A, B, ang);
         rpair_layer_odd<M, true>(A, B, ang, t, T, xs);
@@ -440,7 +451,7 @@ ION_DEVINL void h2_pair(cplx (&A)[M], cplx (&B)[M], const RPairAngles<M> &ang, b
         rpair_layer_odd<M, true>(A, B, ang, t, T, xs);
         rpair_layer_even<M, true>(A, B, ang);
     }
-    hadamard<M>(A, B);
+    hadamard_out<M>(A, B);
 }
 
 // =============================================================================================

@@ -105,22 +105,24 @@ ION_DEVINL void slab_h2(cplx (&A)[4], cplx (&B)[4], const Trig (&ang)[5], bool h
         brick(A[0], A[1], B[0], B[1], ang[1]);
         brick(A[2], A[3], B[2], B[3], ang[3]);
     }
+    // back, again without the 1/sqrt(2): the result is 2 x (h2 psi); the two factors of 2 of stages 1 and 5 are folded into
+    // the mask of stage 3 (every operator in between is linear; powers of two are exact)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const cplx sv = A[j], d = B[j];
-        A[j] = c_make(0.5 * (sv.x + d.x), 0.5 * (sv.y + d.y));
-        B[j] = c_make(0.5 * (sv.x - d.x), 0.5 * (sv.y - d.y));
+        A[j] = c_add(sv, d);
+        B[j] = c_sub(sv, d);
     }
 }
 
 // the five r-pair angles of one l-pair: four evaluations, the pair shared with the previous row group comes from the
 // neighbouring lane (its ang[4])
-ION_DEVINL void slab_h2_angles(Trig (&ang)[5], const double (&z)[5], double kappa)
+ION_DEVINL void slab_h2_angles(Trig (&ang)[5], const double (&z)[5], double kappa, double zmax)
 {
     double th[4], sn[4], cs[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) th[j] = kappa * z[j + 1];
-    fast_sincos_n<4>(th, sn, cs);
+    fast_sincos_n_bounded<4>(th, sn, cs, fabs(kappa) * zmax);
 #pragma unroll
     for (int j = 0; j < 4; ++j) ang[j + 1].c = cs[j], ang[j + 1].s = sn[j];
     ang[0].c = __shfl_up_sync(0xffffffffu, cs[3], 1);
@@ -128,12 +130,12 @@ ION_DEVINL void slab_h2_angles(Trig (&ang)[5], const double (&z)[5], double kapp
 }
 
 template <int N>
-ION_DEVINL void slab_angles(Trig (&ang)[N], const double (&v)[N], double kappa)
+ION_DEVINL void slab_angles(Trig (&ang)[N], const double (&v)[N], double kappa, double vmax)
 {
     double th[N], sn[N], cs[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) th[j] = kappa * v[j];
-    fast_sincos_n<N>(th, sn, cs);
+    fast_sincos_n_bounded<N>(th, sn, cs, fabs(kappa) * vmax);
 #pragma unroll
     for (int j = 0; j < N; ++j) ang[j].c = cs[j], ang[j].s = sn[j];
 }
@@ -189,13 +191,15 @@ __global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
         const int r = r0 + j;
         const bool ok = r >= 0 && r < p.R;
         v[j] = ok ? p.vec[slab_pos(r, T)] : 0.0;
-        mk[j] = (ok && p.mask) ? p.mask[slab_pos(r, T)] : 1.0;
+        mk[j] = 0.25 * ((ok && p.mask) ? p.mask[slab_pos(r, T)] : 1.0);  // 1/4: the unnormalised Hadamard pairs of stages 1 and 5
     }
+    const double vmax = fmax(fmax(fabs(v[0]), fabs(v[1])), fmax(fabs(v[2]), fabs(v[3])));
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         const int r = r0 - 1 + j;  // lower row of the pair
         z[j] = (r >= 0 && r + 1 < p.R) ? p.zvec[slab_pos(r, T)] : 0.0;
     }
+    const double zmax = fmax(fmax(fabs(z[1]), fabs(z[2])), fmax(fabs(z[3]), fabs(z[4])));
     const double sa = p.scal_a[b], sb = p.scal_b[b];
     auto coef = [&](const double *c, int l) -> double { return (q_ok && l >= 0 && l + 1 < L) ? c[l] : 0.0; };
     const bool has_prev = g > 0, has_next = g + 1 < G;
@@ -219,9 +223,9 @@ __global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
     // ---- stage 1: h2 (reversed) on (0,1), (2,3) with s_a ----
     {
         Trig ang[5];
-        slab_h2_angles(ang, z, sa * coef(p.cl2, l0));
+        slab_h2_angles(ang, z, sa * coef(p.cl2, l0), zmax);
         slab_h2<true>(X[0], X[1], ang, has_prev, has_next);
-        slab_h2_angles(ang, z, sa * coef(p.cl2, l0 + 2));
+        slab_h2_angles(ang, z, sa * coef(p.cl2, l0 + 2), zmax);
         slab_h2<true>(X[2], X[3], ang, has_prev, has_next);
     }
     // ---- stages 2 and 4: odd l-pairs; stage 3 in between ----
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
     for (int pass = 0; pass < 2; ++pass) {
         const double s = pass == 0 ? sa : sb;
         Trig ang_up[4];  // pair (l0 + 3, l0 + 4): evaluated here, handed to the next quad's thread with the edge channel
-        slab_angles<4>(ang_up, v, s * coef(p.cl, l0 + 3));
+        slab_angles<4>(ang_up, v, s * coef(p.cl, l0 + 3), vmax);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             xch[(0 * 4 + j) * NT + tid] = X[0][j];
@@ -240,7 +244,7 @@ __global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
         __syncthreads();
         {
             Trig ang[4];
-            slab_angles<4>(ang, v, s * coef(p.cl, l0 + 1));
+            slab_angles<4>(ang, v, s * coef(p.cl, l0 + 1), vmax);
             slab_rot(X[1], X[2], ang);
         }
         if (ql > 0) {  // pair (l0 - 1, l0): my channel 0 is the upper member
@@ -263,9 +267,9 @@ __global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
         if (pass == 0) {
             // ---- stage 3: even l-pairs by s_a + s_b, mask ----
             Trig ang[4];
-            slab_angles<4>(ang, v, (sa + sb) * coef(p.cl, l0));
+            slab_angles<4>(ang, v, (sa + sb) * coef(p.cl, l0), vmax);
             slab_rot(X[0], X[1], ang);
-            slab_angles<4>(ang, v, (sa + sb) * coef(p.cl, l0 + 2));
+            slab_angles<4>(ang, v, (sa + sb) * coef(p.cl, l0 + 2), vmax);
             slab_rot(X[2], X[3], ang);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -278,9 +282,9 @@ __global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
     // ---- stage 5: h2 (forward) on (0,1), (2,3) with s_b ----
     {
         Trig ang[5];
-        slab_h2_angles(ang, z, sb * coef(p.cl2, l0));
+        slab_h2_angles(ang, z, sb * coef(p.cl2, l0), zmax);
         slab_h2<false>(X[0], X[1], ang, has_prev, has_next);
-        slab_h2_angles(ang, z, sb * coef(p.cl2, l0 + 2));
+        slab_h2_angles(ang, z, sb * coef(p.cl2, l0 + 2), zmax);
         slab_h2<false>(X[2], X[3], ang, has_prev, has_next);
     }
 
