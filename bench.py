@@ -47,6 +47,17 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full capture of this
+    workload (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep); None when no capture is on file."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            entry = json.load(f)[workload][kernel]
+        return float(entry["dram_bytes_read"]) + float(entry["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def build_workload(name):
     """-> (problem, description[, batch, fields[n_steps, batch]])"""
     from ionization_b200 import configs
@@ -336,8 +347,10 @@ def main():
             steps_per_launch = n_prof / dom_n if dom == "resident" else 1.0
             alg_bytes = BYTES_PER_UPDATE * L * R * batch * steps_per_launch
             achieved = alg_bytes / (dom_ms / dom_n * 1e-3) / 1e9
+            kname = {"resident": "k_resident", "slab": "k_slab", "adi_l": "k_adi_l"}.get(dom, f"k_unit<{dom}>")
             roofline = {
-                "bound": "hbm", "kernel": {"resident": "k_resident", "slab": "k_slab", "adi_l": "k_adi_l"}.get(dom, f"k_unit<{dom}>"), "time_steps_per_launch": steps_per_launch, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "bound": "hbm", "kernel": kname, "time_steps_per_launch": steps_per_launch, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(args.workload, kname),
                 "peak_source": peak_src, "avg_launch_us": 1e3 * dom_ms / dom_n, "share_of_step": dom_ms / total_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "kernels_us": {k: round(1e3 * v[0] / v[1], 3) for k, v in prof.items()},

@@ -46,7 +46,7 @@ extern "C" {
 #define ION_LINE_LEN_CN 2 /* LineLengthGaugeOperators + AlternatingDirectionImplicit            (mesh_operators.py:304-349, evolution_methods.py:46-77) */
 #define ION_LINE_LEN_SO 3 /* LineLengthGaugeOperators + SplitInteractionOperator                (mesh_operators.py:329-341)                              */
 #define ION_LINE_VEL_SO 4 /* LineVelocityGaugeOperators + SplitInteractionOperator              (mesh_operators.py:352-427)                              */
-#define ION_SH_LEN_ADI 5  /* SphericalHarmonicLengthGaugeOperators + AlternatingDirectionImplicit (evolution_methods.py:46-77; SURVEY 8f-4, "next")       */
+#define ION_SH_LEN_ADI 5  /* SphericalHarmonicLengthGaugeOperators + AlternatingDirectionImplicit (evolution_methods.py:46-77, mesh_operators.py:1020-1035); unsharded, l_bound <= 4096 */
 
 /* observables computed by ion_sim_observe / ion_sim_run (bit mask) */
 #define ION_OBS_NORM 1u            /* QuantumMesh.norm                    mesh/meshes.py:215-217          */

@@ -15,10 +15,10 @@
 //     8c .. 8c+7 of position q in registers.  With s = tau E x_j and beta_l = s c_l the matrix is 1 on the diagonal and
 //     i beta_l off it, so its pivots are REAL: p_l = 1 + beta_{l-1}^2 / p_{l-1}.  w_l = 1/p_l obeys the Moebius map
 //     w -> 1 / (1 + a w); every thread composes its 8 maps into one 2x2 real matrix, the chunk inflows follow from a
-//     sequential walk over the preceding chunks' matrices in shared memory (one division per chunk), exactly.
-//     Forward / backward substitution are affine recurrences with multipliers -i beta w: zero-inflow pass, chunk
-//     aggregates to shared memory, sequential prefix over the preceding (following) chunks, second pass with the true
-//     inflow -- the same scheme as the radial Crank-Nicolson scans (kernels.cuh), across chunks instead of lanes;
+//     two-level prefix (shuffles over the chunks a warp holds, then a walk over the warp totals in shared memory), exactly.
+//     Forward / backward substitution are affine recurrences with multipliers -i beta w: zero-inflow pass, two-level prefix
+//     of the chunk aggregates, second pass with the true inflow -- the same scheme as the radial Crank-Nicolson scans
+//     (kernels.cuh), across chunks instead of lanes;
 //   * (1 - i tau H_int)(1 + i tau H_int)^-1 v = 2 (1 + i tau H_int)^-1 v - v: no second mat-vec.
 // The remaining (1 + i tau H0)^-1_r and the mask are k_unit<PROG_CN> with F_SOLVE_ONLY | F_MASK.
 // PW = 8 positions are one full 128-byte line per channel; L <= 8 * 512 channels.
@@ -47,6 +47,86 @@ ION_DEVINL cplx mul_mi(double e, cplx v) { return c_make(e * v.y, -e * v.x); }
 // (-i e) v + a
 ION_DEVINL cplx fma_mi(double e, cplx v, cplx a) { return c_make(fma(e, v.y, a.x), fma(-e, v.x, a.y)); }
 
+// ---- two-level prefixes over the chunks of one radial position ----------------------------------------------------
+// Threads of the same position q sit PW lanes apart; a warp holds CPW = 32 / PW consecutive chunks of each of its positions.
+// Level 1: Kogge-Stone over those chunks with shuffles (stride PW).  Level 2: the warp totals go to shared memory and every
+// thread walks over the totals of the preceding (following) warps -- at most 15 steps instead of one per chunk.
+
+// affine maps v -> M v + Y.  Returns the value entering this thread's chunk; sm: 4 * nw * PW doubles.
+template <bool FWD>
+ION_DEVINL cplx adi_affine_inflow(cplx M, cplx Y, double *sm, int PW, int tid, int nthreads)
+{
+    const int lane = tid & 31, warp = tid >> 5, nw = nthreads >> 5, q = lane % PW, stride = nw * PW;
+    for (int s = PW; s < 32; s <<= 1) {
+        const cplx Mp = FWD ? shfl_up_c(M, s) : shfl_down_c(M, s);
+        const cplx Yp = FWD ? shfl_up_c(Y, s) : shfl_down_c(Y, s);
+        if (FWD ? (lane >= s) : (lane + s < 32)) {
+            Y = c_fma(M, Yp, Y);
+            M = c_mul(M, Mp);
+        }
+    }
+    if (FWD ? (lane >= 32 - PW) : (lane < PW)) {
+        const int j = warp * PW + q;
+        sm[0 * stride + j] = M.x;
+        sm[1 * stride + j] = M.y;
+        sm[2 * stride + j] = Y.x;
+        sm[3 * stride + j] = Y.y;
+    }
+    __syncthreads();
+    cplx v = c_zero();
+    if (FWD) {
+        for (int w = 0; w < warp; ++w) {
+            const int j = w * PW + q;
+            v = c_fma(c_make(sm[0 * stride + j], sm[1 * stride + j]), v, c_make(sm[2 * stride + j], sm[3 * stride + j]));
+        }
+    } else {
+        for (int w = nw - 1; w > warp; --w) {
+            const int j = w * PW + q;
+            v = c_fma(c_make(sm[0 * stride + j], sm[1 * stride + j]), v, c_make(sm[2 * stride + j], sm[3 * stride + j]));
+        }
+    }
+    __syncthreads();  // sm is reused by the next phase
+    // exclusive inside the warp: the inclusive map of the neighbouring chunk applied to the warp's inflow
+    const cplx Me = FWD ? shfl_up_c(M, PW) : shfl_down_c(M, PW);
+    const cplx Ye = FWD ? shfl_up_c(Y, PW) : shfl_down_c(Y, PW);
+    const bool first = FWD ? (lane < PW) : (lane >= 32 - PW);
+    return first ? v : c_fma(Me, v, Ye);
+}
+
+// Moebius maps w -> (A w + B) / (C w + D) with non-negative real entries (forward only).  Products are renormalised (a Moebius map
+// is projective), so long runs of channels cannot overflow.  Returns the value entering this thread's chunk (start value 1).
+ION_DEVINL double adi_moebius_inflow(double A, double B, double C, double D, double *sm, int PW, int tid, int nthreads)
+{
+    const int lane = tid & 31, warp = tid >> 5, nw = nthreads >> 5, q = lane % PW, stride = nw * PW;
+    for (int s = PW; s < 32; s <<= 1) {
+        const double Ap = __shfl_up_sync(0xffffffffu, A, s), Bp = __shfl_up_sync(0xffffffffu, B, s);
+        const double Cp = __shfl_up_sync(0xffffffffu, C, s), Dp = __shfl_up_sync(0xffffffffu, D, s);
+        if (lane >= s) {  // mine * previous
+            const double nA = fma(A, Ap, B * Cp), nB = fma(A, Bp, B * Dp), nC = fma(C, Ap, D * Cp), nD = fma(C, Bp, D * Dp);
+            const double sc = 1.0 / (nA + nB + nC + nD);
+            A = nA * sc, B = nB * sc, C = nC * sc, D = nD * sc;
+        }
+    }
+    if (lane >= 32 - PW) {
+        const int j = warp * PW + q;
+        sm[0 * stride + j] = A;
+        sm[1 * stride + j] = B;
+        sm[2 * stride + j] = C;
+        sm[3 * stride + j] = D;
+    }
+    __syncthreads();
+    double v = 1.0;
+    for (int w = 0; w < warp; ++w) {
+        const int j = w * PW + q;
+        v = fma(sm[0 * stride + j], v, sm[1 * stride + j]) / fma(sm[2 * stride + j], v, sm[3 * stride + j]);
+    }
+    __syncthreads();
+    const double Ae = __shfl_up_sync(0xffffffffu, A, PW), Be = __shfl_up_sync(0xffffffffu, B, PW);
+    const double Ce = __shfl_up_sync(0xffffffffu, C, PW), De = __shfl_up_sync(0xffffffffu, D, PW);
+    return lane < PW ? v : fma(Ae, v, Be) / fma(Ce, v, De);
+}
+
+// grid = (Rp / PW, batch); block = PW * NC rounded up to whole warps (threads beyond chunk NC - 1 hold no channels)
 __global__ void __launch_bounds__(ADI_MAX_THREADS, 1) k_adi_l(const AdiParams p)
 {
     constexpr int CL = ADI_CL;
@@ -91,6 +171,7 @@ __global__ void __launch_bounds__(ADI_MAX_THREADS, 1) k_adi_l(const AdiParams p)
         bq[k] = (l >= 1 && l < L) ? s * p.cl[l - 1] : 0.0;
     }
     // Moebius chunk matrix of w -> 1 / (1 + a w):  [[0, 1], [a, 1]] per channel, later channels on the left
+    double w_in;
     {
         double A = 1.0, B = 0.0, C = 0.0, D = 1.0;
 #pragma unroll
@@ -104,19 +185,8 @@ __global__ void __launch_bounds__(ADI_MAX_THREADS, 1) k_adi_l(const AdiParams p)
                 B = nB;
             }
         }
-        sm[0 * NT + tid] = A;
-        sm[1 * NT + tid] = B;
-        sm[2 * NT + tid] = C;
-        sm[3 * NT + tid] = D;
+        w_in = adi_moebius_inflow(A, B, C, D, sm, p.PW, tid, NT);  // irrelevant for chunk 0 (its first coupling is zero)
     }
-    __syncthreads();
-    double w_in = 1.0;  // irrelevant for chunk 0 (its first coupling is zero)
-    for (int kk = 0; kk < c; ++kk) {
-        const int j = kk * p.PW + q;
-        const double A = sm[0 * NT + j], B = sm[1 * NT + j], C = sm[2 * NT + j], D = sm[3 * NT + j];
-        w_in = fma(A, w_in, B) / fma(C, w_in, D);
-    }
-    __syncthreads();
     double w[CL];
     {
         double wp = w_in;
@@ -151,6 +221,7 @@ __global__ void __launch_bounds__(ADI_MAX_THREADS, 1) k_adi_l(const AdiParams p)
     ef[0] = bq[0] * w_in;
 #pragma unroll
     for (int k = 1; k < CL; ++k) ef[k] = bq[k] * w[k - 1];
+    cplx yin;
     {
         cplx z = g1[0], m = c_make(0.0, -ef[0]);
 #pragma unroll
@@ -158,18 +229,8 @@ __global__ void __launch_bounds__(ADI_MAX_THREADS, 1) k_adi_l(const AdiParams p)
             z = fma_mi(ef[k], z, g1[k]);
             m = mul_mi(ef[k], m);
         }
-        sm[0 * NT + tid] = m.x;
-        sm[1 * NT + tid] = m.y;
-        sm[2 * NT + tid] = z.x;
-        sm[3 * NT + tid] = z.y;
+        yin = adi_affine_inflow<true>(m, z, sm, p.PW, tid, NT);
     }
-    __syncthreads();
-    cplx yin = c_zero();
-    for (int kk = 0; kk < c; ++kk) {
-        const int j = kk * p.PW + q;
-        yin = c_fma(c_make(sm[0 * NT + j], sm[1 * NT + j]), yin, c_make(sm[2 * NT + j], sm[3 * NT + j]));
-    }
-    __syncthreads();
     cplx y[CL];
     y[0] = fma_mi(ef[0], yin, g1[0]);
 #pragma unroll
@@ -179,6 +240,7 @@ __global__ void __launch_bounds__(ADI_MAX_THREADS, 1) k_adi_l(const AdiParams p)
     double eb[CL];
 #pragma unroll
     for (int k = 0; k < CL; ++k) eb[k] = bq[k + 1] * w[k];
+    cplx xin;
     {
         cplx z = c_scale(y[CL - 1], w[CL - 1]), m = c_make(0.0, -eb[CL - 1]);
 #pragma unroll
@@ -186,16 +248,7 @@ __global__ void __launch_bounds__(ADI_MAX_THREADS, 1) k_adi_l(const AdiParams p)
             z = fma_mi(eb[k], z, c_scale(y[k], w[k]));
             m = mul_mi(eb[k], m);
         }
-        sm[0 * NT + tid] = m.x;
-        sm[1 * NT + tid] = m.y;
-        sm[2 * NT + tid] = z.x;
-        sm[3 * NT + tid] = z.y;
-    }
-    __syncthreads();
-    cplx xin = c_zero();
-    for (int kk = p.NC - 1; kk > c; --kk) {
-        const int j = kk * p.PW + q;
-        xin = c_fma(c_make(sm[0 * NT + j], sm[1 * NT + j]), xin, c_make(sm[2 * NT + j], sm[3 * NT + j]));
+        xin = adi_affine_inflow<false>(m, z, sm, p.PW, tid, NT);
     }
     // true inflow; out = 2 x - g1 = (1 - i tau H_int) x
     cplx x = xin;

@@ -665,7 +665,7 @@ int launch_adi_l(ion_sim *s, const double *sa)
     cudaLaunchConfig_t cfg;
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(s->Rp / pw, s->batch);
-    cfg.blockDim = dim3(pw * p.NC);
+    cfg.blockDim = dim3((pw * p.NC + 31) / 32 * 32);  // whole warps: the prefixes shuffle
     cfg.dynamicSmemBytes = 0;
     cfg.stream = s->stream;
     cudaLaunchAttribute attr[1];
