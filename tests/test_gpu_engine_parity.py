@@ -445,3 +445,59 @@ def test_adi_chunk_geometries_against_oracle(L, R):
         g = sim.read_g()[0]
     ref = restate.run_sh(p, store_every_step=False)
     assert rel_err(g, ref["g"]) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases: tiny and ragged meshes, empty calls, step-by-step driving
+# ---------------------------------------------------------------------------------------------
+def _random_problem(kind, L, R, n_steps, seed=0):
+    """a seeded synthetic problem of the fixtures' layout (random H0 with the reference's structure: real diagonal, constant-sign
+    off-diagonal), checked against the oracle on the same inputs"""
+    rng = np.random.default_rng(seed)
+    p = dict(kind=kind, L=L, R=R, r=np.linspace(0.05, 0.05 + 0.1 * (R - 1), R), delta_r=0.1)
+    p["h_diag"] = (rng.uniform(0.5, 3.0, (L, R)) + 0.0j)
+    p["h_off"] = -rng.uniform(0.4, 0.6, R - 1)
+    p["mask"] = np.cos(np.linspace(0, 1.2, R)) ** 0.125
+    g0 = rng.standard_normal((L, R)) + 1j * rng.standard_normal((L, R))
+    p["g0"] = g0 / np.sqrt(np.sum(np.abs(g0) ** 2) * 0.1)
+    p["taus"] = np.full(n_steps, 0.05)
+    p["fields"] = rng.uniform(-1, 1, n_steps)
+    p["c_l"] = rng.uniform(0.3, 0.6, max(L - 1, 0))
+    if kind == "sh_vel_so":
+        p["f1_l"] = rng.uniform(0.5, 5.0, max(L - 1, 0))
+        p["y_j"] = rng.uniform(0.01, 1.0, R)
+        p["z_j"] = rng.uniform(0.01, 0.5, R - 1)
+    else:
+        p["x_j"] = rng.uniform(0.0, 2.0, R)
+    return p
+
+
+@pytest.mark.parametrize("kind", ["sh_len_so", "sh_vel_so", "sh_len_adi"])
+@pytest.mark.parametrize("L,R", [(1, 8), (2, 2), (2, 5), (3, 33), (4, 129), (5, 127), (17, 4), (8, 1025)])
+def test_tiny_and_ragged_meshes_against_oracle(kind, L, R):
+    from oracle import restate
+
+    eng = _engine()
+    p = _random_problem(kind, L, R, 7)
+    with eng.DeviceSimulation.from_problem(p, with_states=False) as sim:
+        sim.step(p["taus"], p["fields"])
+        g = sim.read_g()[0]
+        norm = sim.observe(eng.nat.OBS_NORM)[0, 0]
+    ref = restate.run_sh(p, store_every_step=False)
+    assert rel_err(g, ref["g"]) < TOL
+    assert abs(norm - ref["norm"][-1]) < TOL * max(1.0, ref["norm"][-1])
+
+
+@pytest.mark.parametrize("kind", ["sh_len_so", "sh_vel_so", "sh_len_adi"])
+def test_empty_call_and_step_by_step_equal_one_call(kind):
+    """n_steps = 0 is a no-op; driving the engine one step per call (the callback path of MeshSimulation.run, mesh/sims.py:307)
+    gives the same wavefunction as one call (the fused schedules differ, the arithmetic may differ in the last bits)."""
+    eng = _engine()
+    p = _random_problem(kind, 6, 70, 9, seed=3)
+    with eng.DeviceSimulation.from_problem(p, with_states=False) as a, eng.DeviceSimulation.from_problem(p, with_states=False) as b:
+        a.step(p["taus"][:0], p["fields"][:0])
+        assert rel_err(a.read_g()[0], p["g0"]) < 1e-15
+        a.step(p["taus"], p["fields"])
+        for n in range(len(p["taus"])):
+            b.step(p["taus"][n : n + 1], p["fields"][n : n + 1])
+        assert rel_err(a.read_g()[0], b.read_g()[0]) < 1e-13
