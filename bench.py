@@ -58,6 +58,16 @@ def ncu_traffic(workload, kernel):
         return None
 
 
+def ncu_traffic_warm(workload, kernel):
+    """the same from the capture without cache flushes between replays (the L2-resident steady state), if on file"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            entry = json.load(f)[workload][kernel]
+        return float(entry["warm_dram_bytes_read"]) + float(entry["warm_dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def build_workload(name):
     """-> (problem, description[, batch, fields[n_steps, batch]])"""
     from ionization_b200 import configs
@@ -350,7 +360,7 @@ def main():
             kname = {"resident": "k_resident", "slab": "k_slab", "adi_l": "k_adi_l"}.get(dom, f"k_unit<{dom}>")
             roofline = {
                 "bound": "hbm", "kernel": kname, "time_steps_per_launch": steps_per_launch, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.workload, kname),
+                "traffic": ncu_traffic(args.workload, kname), "traffic_warm_l2": ncu_traffic_warm(args.workload, kname),
                 "peak_source": peak_src, "avg_launch_us": 1e3 * dom_ms / dom_n, "share_of_step": dom_ms / total_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "kernels_us": {k: round(1e3 * v[0] / v[1], 3) for k, v in prof.items()},
