@@ -357,7 +357,7 @@ def main():
             steps_per_launch = n_prof / dom_n if dom == "resident" else 1.0
             alg_bytes = BYTES_PER_UPDATE * L * R * batch * steps_per_launch
             achieved = alg_bytes / (dom_ms / dom_n * 1e-3) / 1e9
-            kname = {"resident": "k_resident", "slab": "k_slab", "adi_l": "k_adi_l"}.get(dom, f"k_unit<{dom}>")
+            kname = {"resident": "k_resident", "slab": "k_slab", "adi_l": "k_adi_l", "len_ens": "k_len_ens"}.get(dom, f"k_unit<{dom}>")
             roofline = {
                 "bound": "hbm", "kernel": kname, "time_steps_per_launch": steps_per_launch, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(args.workload, kname), "traffic_warm_l2": ncu_traffic_warm(args.workload, kname),

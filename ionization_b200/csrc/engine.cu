@@ -27,6 +27,7 @@
 #include "resident.cuh"
 #include "slab.cuh"
 #include "adi.cuh"
+#include "ensemble.cuh"
 #include "halo.cuh"
 
 namespace {
@@ -64,12 +65,13 @@ enum KernelKind : int {
     KK_LEN_STEP,
     KK_HALO,
     KK_ADI_L,
+    KK_LEN_ENS,
     KK_COUNT
 };
 const char *const kKernelNames[KK_COUNT] = {"rot",        "rot_cn_rot", "h2",        "h2_cn_h2", "cn",     "line_so_len",
                                             "line_so_vel", "line_cn",    "sweep_flat", "mask",    "observe",
                                             "resident",    "slab",       "len_step",   "halo",
-                                            "adi_l"};
+                                            "adi_l",       "len_ens"};
 
 template <typename T>
 int dev_alloc(T **p, size_t n)
@@ -111,6 +113,9 @@ struct ion_sim {
     void *peer_ipc_base[2] = {nullptr, nullptr};    // IPC mappings to close
     bool peers_attached = false;
     bool use_len_fold = true;
+    bool use_ens = true;
+    int ens_state = 0;  // scan ensembles: persistent folded length-gauge kernel with a prefetch pipeline (ensemble.cuh); 0 / 1 / -1 as above
+    int ens_ctas = 0;
     int len_fold_state = 0;  // length gauge: even sweep folded into the out-of-place PROG_LEN_STEP kernel (0 / 1 / -1 as above)
     int slab_G = 0, slab_slabs = 0, slab_chunks = 0, slab_Qc = 0, slab_nQ = 0, slab_threads = 0;
     cplx *h_diag = nullptr;
@@ -339,8 +344,12 @@ ion::UnitParams base_params(ion_sim *s)
     p.H = s->H;
     p.l_begin = s->l_begin;
     p.short_scan = s->short_scan;
+    p.unit0 = 0;
+    p.unit_stride = 1;
     return p;
 }
+
+int launch_len_ens(ion_sim *s, const ion::UnitParams &p);
 
 int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, const double *sb)
 {
@@ -413,8 +422,12 @@ int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, c
         case ion::PROG_LEN_STEP:
             kind = KK_LEN_STEP;
             p.psi_out = s->psi2;
-            prof_begin(s, kind);
-            rc = launch_unit_prog<ion::PROG_LEN_STEP>(s, p, grid);
+            if (s->ens_state == 1) {
+                rc = launch_len_ens(s, p);
+            } else {
+                prof_begin(s, kind);
+                rc = launch_unit_prog<ion::PROG_LEN_STEP>(s, p, grid);
+            }
             std::swap(s->psi, s->psi2);
             break;
         default: return fail(ION_EINVAL, "unknown unit program");
@@ -566,7 +579,51 @@ int len_fold_prepare(ion_sim *s)
     if (s->L_own != s->L_total || s->L < 2) return ION_OK;
     if (int rc = ensure_second_buffer(s)) return rc;
     s->len_fold_state = 1;
+    // ensembles: persistent CTAs with a prefetch pipeline instead of one short-lived CTA per (pair, member)
+    s->ens_state = -1;
+    if (s->use_ens && s->M == 4 && s->S == 1 && s->T == ion::ENS_T && s->L >= 4 && !s->peers_attached) {
+        const long long tasks = (long long)s->batch * (s->L / 2 - 1);
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
+        const int slots = 2 * prop.multiProcessorCount;
+        if (tasks >= 4LL * slots) {
+            CUDA_TRY(cudaFuncSetAttribute(ion::k_len_ens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ion::ens_smem_bytes()));
+            int per_sm = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ion::k_len_ens, ion::ENS_T, ion::ens_smem_bytes()));
+            if (per_sm >= 1) {
+                s->ens_ctas = per_sm * prop.multiProcessorCount;
+                s->ens_state = 1;
+            }
+        }
+    }
     return ION_OK;
+}
+
+// the folded length-gauge step of an ensemble: persistent kernel over the channel pairs + k_unit over the two single channels
+int launch_len_ens(ion_sim *s, const ion::UnitParams &p)
+{
+    const int n_pairs = s->L / 2 - 1;
+    const long long n_tasks = (long long)s->batch * n_pairs;
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)std::min<long long>(n_tasks, s->ens_ctas));
+    cfg.blockDim = dim3(ion::ENS_T);
+    cfg.dynamicSmemBytes = ion::ens_smem_bytes();
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = s->use_pdl ? 1 : 0;
+    prof_begin(s, KK_LEN_ENS);
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_len_ens, p, n_pairs, n_tasks));
+    prof_end(s);
+    s->launch_count++;
+    ion::UnitParams q = p;  // l = 0 and l = L - 1: units 0 and L/2 of the odd sweep
+    q.unit0 = 0;
+    q.unit_stride = s->L / 2;
+    prof_begin(s, KK_LEN_STEP);
+    return launch_unit_prog<ion::PROG_LEN_STEP>(s, q, dim3(2, s->batch));
 }
 
 int slab_prepare(ion_sim *s)
@@ -1269,6 +1326,7 @@ int ion_sim_create_sharded(int program, int64_t L_total, int64_t l_begin, int64_
     if (const char *env = std::getenv("ION_NO_RESIDENT")) s->use_resident = s->use_resident && !(env[0] == '1');
     if (const char *env = std::getenv("ION_NO_SLAB")) s->use_slab = !(env[0] == '1');
     if (const char *env = std::getenv("ION_NO_LEN_FOLD")) s->use_len_fold = !(env[0] == '1');
+    if (const char *env = std::getenv("ION_NO_ENS")) s->use_ens = !(env[0] == '1');
     int rc = prepare_kernels(s);
     if (rc == ION_OK) rc = dev_alloc(&s->psi, (size_t)batch * L * s->Rp);
     if (rc == ION_OK) {

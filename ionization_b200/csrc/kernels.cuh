@@ -52,6 +52,7 @@ struct UnitParams {
     int parity;              // parity (in GLOBAL l) of the lower channel of a pair
     int flags;
     int short_scan;          // reach of the cross-warp inflow of the CN scans in warps (0: full scan; see common.cuh)
+    int unit0, unit_stride;  // unit of CTA x = unit0 + x * unit_stride (0, 1: all units; the ensemble kernel leaves the single channels to k_unit)
 };
 
 // unit -> (first local channel, is pair).  Pairs are (l, l+1) with global l % 2 == parity.
@@ -588,7 +589,7 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
     const int tl = threadIdx.x, Tc = blockDim.x;         // index inside the CTA: scans and exchanges
     const int T = p.T;                                   // row stride of the layout
     // SEG == false (one CTA per channel, the common case): all of this folds away at compile time
-    const int seg = SEG ? (int)(blockIdx.x % p.S) : 0, unit = SEG ? (int)(blockIdx.x / p.S) : (int)blockIdx.x;
+    const int seg = SEG ? (int)(blockIdx.x % p.S) : 0, unit = p.unit0 + (SEG ? (int)(blockIdx.x / p.S) : (int)blockIdx.x) * p.unit_stride;
     const int t = SEG ? seg * p.T_seg - p.H + tl : tl;   // thread index inside the channel: addressing
     const bool ok = SEG ? ((t >= 0) && (t < T)) : true;
     const bool mine = SEG ? (ok && (tl >= p.H) && (tl < p.H + p.T_seg)) : true;

@@ -501,3 +501,34 @@ def test_empty_call_and_step_by_step_equal_one_call(kind):
         for n in range(len(p["taus"])):
             b.step(p["taus"][n : n + 1], p["fields"][n : n + 1])
         assert rel_err(a.read_g()[0], b.read_g()[0]) < 1e-13
+
+
+def test_ensemble_persistent_prefetch_kernel_matches_one_cta_per_task(monkeypatch):
+    """csrc/ensemble.cuh: scan ensembles with at least four waves of (pair, member) tasks run the folded length-gauge step in
+    persistent CTAs with a cp.async prefetch pipeline.  Same arithmetic as k_unit<LEN_STEP>: compared with that path
+    (ION_NO_ENS=1), with sparse observations in between, and member by member with the oracle."""
+    from ionization_b200 import configs, units as u
+    from oracle import restate
+
+    eng = _engine()
+    p = configs.spherical_harmonic_problem(r_bound=100 * u.bohr_radius, r_points=1000, l_bound=8, gauge="LEN", n_steps=14)
+    batch, n = 400, len(p["taus"])
+    rng = np.random.default_rng(5)
+    scale = rng.uniform(-3, 3, batch)
+    fields = (np.asarray(p["fields"]) + 2e10)[:, None] * scale[None, :]
+    mask = np.zeros(n, dtype=np.uint8)
+    mask[4::5] = 1
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("ION_NO_ENS", flag)
+        with eng.DeviceSimulation.from_problem(p, batch=batch) as sim:
+            rec = sim.run(p["taus"], fields, mask, eng.nat.OBS_NORM)
+            out[flag] = (sim.read_g(), rec, sim.launch_count)
+    assert rel_err(out["0"][0], out["1"][0]) < 1e-13
+    assert np.max(np.abs(out["0"][1] - out["1"][1])) < 1e-13
+    assert out["0"][2] != out["1"][2]  # the persistent path really ran (it adds a launch for the two single channels)
+    for b in (0, 7, batch - 1):
+        q = dict(p)
+        q["fields"] = fields[:, b]
+        ref = restate.run_sh(q, store_every_step=False)
+        assert rel_err(out["0"][0][b], ref["g"]) < TOL
