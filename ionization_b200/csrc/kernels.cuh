@@ -666,12 +666,47 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
     // ---- programs containing Crank-Nicolson ----
     // pairs: both channels are solved together in layout 2 (see above); single channels and r-segments keep layout 1
     constexpr bool L2CN = (M == 4) && !SEG && (TMAX <= 512) && (PROG == PROG_ROT_CN_ROT || PROG == PROG_H2_CN_H2 || PROG == PROG_LEN_STEP);
+#ifdef ION_EXP_CLOCKS  // timing-only instrumentation: phase time stamps of two CTAs (first and second wave)
+    long long ck[8];
+#define ION_CK(i) ck[i] = clock64()
+#else
+#define ION_CK(i)
+#endif
+    ION_CK(0);
     cplx *obase = p.psi_out + ((size_t)b * p.L + l0) * chan;
     if constexpr (L2CN) if (pair) {
         cplx *wsm = xs + 4 * Tc;                                  // [8][Tc]   LU factors, row k of the thread's chunk at wsm[k * Tc + tl]
         double *tosm = reinterpret_cast<double *>(wsm + 8 * Tc);  // [9][Tc/2] tau*off of the chunk's rows (+ the row before it)
         const int pp = tl >> 1, TH = Tc >> 1;
         const bool odd = (tl & 1) != 0;
+        // The small coefficient loads go FIRST: the 64 KB of LU factors of a 512-thread CTA keep the SM's load path busy for
+        // ~1500 cycles, and everything queued behind them (and the trigonometry that waits for it) would be exposed in every CTA
+        // of a second wave, where no previous kernel's tail hides the prologue.
+        double tov[9];
+        if (!odd) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tov[k] = p.toff[(k & 3) * T + 2 * pp + (k >> 2)];
+            tov[8] = p.toff_prev[2 * pp];
+        }
+        cplx P8, Q8;  // multipliers of the 8-row chunk = product of the two 4-row ones
+        cplx aP0, aP1, aQ0, aQ1;
+        {
+            const size_t ch = (size_t)(l0 + (odd ? 1 : 0)) * T + 2 * pp;
+            aP0 = ld_c(p.aggP + ch), aP1 = ld_c(p.aggP + ch + 1), aQ0 = ld_c(p.aggQ + ch), aQ1 = ld_c(p.aggQ + ch + 1);
+        }
+        double cvec[M], czp = 0.0, kap0, kapA = 0.0, kapB = 0.0;
+        if (PROG == PROG_ROT_CN_ROT || PROG == PROG_LEN_STEP) {
+            load_vec<M>(cvec, p.vec, T, t, true);
+            kap0 = sa * p.cl[p.l_begin + l0];
+            if (PROG == PROG_LEN_STEP) {  // a pair always has both even-pair partners: l0 - 1 and l0 + 2
+                kapA = (sa + sb) * p.cl[p.l_begin + l0 - 1];
+                kapB = (sa + sb) * p.cl[p.l_begin + l0 + 1];
+            }
+        } else {
+            load_vec<M>(cvec, p.zvec, T, t, true);
+            czp = p.zprev[t];
+            kap0 = sa * p.cl2[p.l_begin + l0];
+        }
         {   // coalesced reads of both channels' factors, permuted on the way into shared memory
             const cplx *w0 = p.w + (size_t)l0 * chan + tl;
             cplx *dst = wsm + (size_t)(4 * (tl & 1)) * Tc + (tl & ~1);
@@ -684,31 +719,24 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         }
         if (!odd) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) tosm[k * TH + pp] = p.toff[(k & 3) * T + 2 * pp + (k >> 2)];
-            tosm[8 * TH + pp] = p.toff_prev[2 * pp];
+            for (int k = 0; k < 9; ++k) tosm[k * TH + pp] = tov[k];
         }
-        cplx P8, Q8;  // multipliers of the 8-row chunk = product of the two 4-row ones
-        {
-            const size_t ch = (size_t)(l0 + (odd ? 1 : 0)) * T + 2 * pp;
-            P8 = c_mul(ld_c(p.aggP + ch), ld_c(p.aggP + ch + 1));
-            Q8 = c_mul(ld_c(p.aggQ + ch), ld_c(p.aggQ + ch + 1));
-        }
+        P8 = c_mul(aP0, aP1);
+        Q8 = c_mul(aQ0, aQ1);
         RotAngles<M> rang, eangA, eangB;
         RPairAngles<M> pang;
         if (PROG == PROG_ROT_CN_ROT || PROG == PROG_LEN_STEP) {
-            double vec[M];
-            load_vec<M>(vec, p.vec, T, t, true);
-            rang = rot_angles<M>(vec, sa * p.cl[p.l_begin + l0]);
-            if (PROG == PROG_LEN_STEP) {  // a pair always has both even-pair partners: l0 - 1 and l0 + 2
-                eangA = rot_angles<M>(vec, (sa + sb) * p.cl[p.l_begin + l0 - 1]);
-                eangB = rot_angles<M>(vec, (sa + sb) * p.cl[p.l_begin + l0 + 1]);
+            rang = rot_angles<M>(cvec, kap0);
+            if (PROG == PROG_LEN_STEP) {
+                eangA = rot_angles<M>(cvec, kapA);
+                eangB = rot_angles<M>(cvec, kapB);
             }
         } else {
-            double zv[M];
-            load_vec<M>(zv, p.zvec, T, t, true);
-            pang = rpair_angles<M>(zv, p.zprev[t], sa * p.cl2[p.l_begin + l0]);
+            pang = rpair_angles<M>(cvec, czp, kap0);
         }
+        ION_CK(1);
         pdl_wait();
+        ION_CK(2);
         load_rows<M>(A, base, T, t, true);
         load_rows<M>(B, base + chan, T, t, true);
         if (PROG == PROG_LEN_STEP) {
@@ -729,8 +757,10 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         }
         if (PROG == PROG_ROT_CN_ROT || PROG == PROG_LEN_STEP) rotate_pair<M, false>(A, B, rang);
         else h2_pair<M>(A, B, pang, false, tl, Tc, xs);  // (oe, oo)
+        ION_CK(3);
         cp_async_wait_all();
         __syncthreads();
+        ION_CK(4);
         {
             cplx Z[8];
             pair_transpose_in(A, B, Z, odd);
@@ -738,10 +768,18 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
             cn8(Z, wsm + tl, Tc, tosm + pp, wprev, P8, Q8, tl, Tc, sm_scan, p.short_scan);
             pair_transpose_out(Z, A, B, odd);
         }
+        ION_CK(5);
         if (PROG == PROG_ROT_CN_ROT || PROG == PROG_LEN_STEP) rotate_pair<M, false>(A, B, rang);
         else h2_pair<M>(A, B, pang, true, tl, Tc, xs);  // (oo, oe)
+        ION_CK(6);
         store_rows<M>(A, obase, T, t, true);
         store_rows<M>(B, obase + chan, T, t, true);
+        ION_CK(7);
+#ifdef ION_EXP_CLOCKS
+        if ((tl == 0 || tl == 288) && (blockIdx.x == 3 || blockIdx.x == 200) && blockIdx.y == 0)
+            printf("CK prog %d cta %d t %d: prologue %lld pdlwait %lld load+op1 %lld factorwait %lld cn %lld op2 %lld store %lld total %lld\n", PROG, (int)blockIdx.x, tl,
+                   ck[1] - ck[0], ck[2] - ck[1], ck[3] - ck[2], ck[4] - ck[3], ck[5] - ck[4], ck[6] - ck[5], ck[7] - ck[6], ck[7] - ck[0]);
+#endif
         return;
     }
     double toff[M];
