@@ -183,6 +183,13 @@ __global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
     const int r0 = slab * W - 3 + 4 * g;  // first row of this thread (odd; may be negative or beyond R)
 
     pdl_launch_dependents();
+#ifdef ION_EXP_CLOCKS
+    long long ck[10];
+#define ION_SCK(i) ck[i] = clock64()
+#else
+#define ION_SCK(i)
+#endif
+    ION_SCK(0);
 
     // ---- coefficients of this thread's rows (independent of psi) ----
     double v[4], mk[4], z[5];
@@ -204,31 +211,41 @@ __global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
     auto coef = [&](const double *c, int l) -> double { return (q_ok && l >= 0 && l + 1 < L) ? c[l] : 0.0; };
     const bool has_prev = g > 0, has_next = g + 1 < G;
 
-    // ---- load psi: 4 channels x 4 rows ----
+    // ---- load psi: 4 channels x 4 rows, interleaved with the trigonometry of stage 1 ----
+    // 16 warps issuing 16 loads each saturate the SM's load path for ~2.5 k cycles (the issue itself stalls), so the angles of the
+    // first pair are evaluated before the wait (they overlap the previous kernel's tail), those of the second pair between the two
+    // batches of loads.
     cplx X[4][4];
+    Trig ang01[5], ang23[5];
+    slab_h2_angles(ang01, z, sa * coef(p.cl2, l0), zmax);
+    const double kap23 = sa * coef(p.cl2, l0 + 2);
+    ION_SCK(1);
     pdl_wait();
-    {
-        const cplx *base = p.psi_in + ((size_t)b * L + l0) * 4 * T;
+    ION_SCK(2);
+    const cplx *ibase = p.psi_in + ((size_t)b * L + l0) * 4 * T;
+    auto load_pair = [&](int c0) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = c0; c < c0 + 2; ++c) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int r = r0 + j;
                 const bool ok = q_ok && (l0 + c < L) && r >= 0 && r < p.R;
-                X[c][j] = ok ? ld_c(base + (size_t)c * 4 * T + slab_pos(r, T)) : c_zero();
+                X[c][j] = ok ? ld_c(ibase + (size_t)c * 4 * T + slab_pos(r, T)) : c_zero();
             }
         }
-    }
+    };
+    load_pair(0);
+    asm volatile("" ::: "memory");
+    slab_h2_angles(ang23, z, kap23, zmax);
+    asm volatile("" ::: "memory");
+    load_pair(2);
 
     // ---- stage 1: h2 (reversed) on (0,1), (2,3) with s_a ----
-    {
-        Trig ang[5];
-        slab_h2_angles(ang, z, sa * coef(p.cl2, l0), zmax);
-        slab_h2<true>(X[0], X[1], ang, has_prev, has_next);
-        slab_h2_angles(ang, z, sa * coef(p.cl2, l0 + 2), zmax);
-        slab_h2<true>(X[2], X[3], ang, has_prev, has_next);
-    }
+    ION_SCK(3);
+    slab_h2<true>(X[0], X[1], ang01, has_prev, has_next);
+    slab_h2<true>(X[2], X[3], ang23, has_prev, has_next);
     // ---- stages 2 and 4: odd l-pairs; stage 3 in between ----
+    ION_SCK(4);
     const int up = tid + G, dn = tid - G;  // threads holding the same rows of the next / previous quad
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
@@ -279,27 +296,38 @@ __global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
             __syncthreads();  // everybody has read the stage-2 edges: the exchange buffer may be overwritten
         }
     }
-    // ---- stage 5: h2 (forward) on (0,1), (2,3) with s_b ----
+    // ---- stage 5: h2 (forward) on (0,1), (2,3) with s_b; the first pair's stores are issued before the second pair is computed ----
+    ION_SCK(5);
+    const bool st_ok = q_ok && q >= q_int0 && q < q_int1;
+    cplx *obase = p.psi_out + ((size_t)b * L + l0) * 4 * T;
+    auto store_pair = [&](int c0) {  // the interior: rows with 2 <= 4g + j < 4G - 2 of the interior quads
+        if (!st_ok) return;
+#pragma unroll
+        for (int c = c0; c < c0 + 2; ++c) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = 4 * g + j, r = r0 + j;
+                if (l0 + c < L && idx >= 2 && idx < 4 * G - 2 && r >= 0 && r < p.R) st_c(obase + (size_t)c * 4 * T + slab_pos(r, T), X[c][j]);
+            }
+        }
+    };
     {
         Trig ang[5];
         slab_h2_angles(ang, z, sb * coef(p.cl2, l0), zmax);
         slab_h2<false>(X[0], X[1], ang, has_prev, has_next);
+        ION_SCK(6);
+        store_pair(0);
+        asm volatile("" ::: "memory");
         slab_h2_angles(ang, z, sb * coef(p.cl2, l0 + 2), zmax);
         slab_h2<false>(X[2], X[3], ang, has_prev, has_next);
+        store_pair(2);
     }
-
-    // ---- store the interior: rows with 2 <= 4g + j < 4G - 2 of the interior quads ----
-    if (q_ok && q >= q_int0 && q < q_int1) {
-        cplx *base = p.psi_out + ((size_t)b * L + l0) * 4 * T;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int idx = 4 * g + j, r = r0 + j;
-                if (l0 + c < L && idx >= 2 && idx < 4 * G - 2 && r >= 0 && r < p.R) st_c(base + (size_t)c * 4 * T + slab_pos(r, T), X[c][j]);
-            }
-        }
-    }
+#ifdef ION_EXP_CLOCKS
+    ION_SCK(7);
+    if ((tid == 0 || tid == 300) && (blockIdx.x == 3 || blockIdx.x == 120) && blockIdx.y == 0)
+        printf("SCK cta %d t %d: coef %lld pdlwait %lld loadissue %lld stage1 %lld stages2-4 %lld stage5 %lld store %lld total %lld\n", (int)blockIdx.x, tid,
+               ck[1] - ck[0], ck[2] - ck[1], ck[3] - ck[2], ck[4] - ck[3], ck[5] - ck[4], ck[6] - ck[5], ck[7] - ck[6], ck[7] - ck[0]);
+#endif
 }
 
 }  // namespace ion
