@@ -426,7 +426,7 @@ def test_adi_ensemble_with_different_fields_and_sparse_observations():
         assert np.max(np.abs(rec[:, b, 0] - ref["norm"][1:][mask.astype(bool)])) < TOL
 
 
-@pytest.mark.parametrize("L,R", [(70, 150), (513, 40), (9, 4100)])
+@pytest.mark.parametrize("L,R", [(70, 150), (513, 40), (9, 4100), (8, 4100), (6, 1000)])
 def test_adi_chunk_geometries_against_oracle(L, R):
     """l-pass thread geometries: several chunks per position with PW = 32 / 4 positions per CTA, and an r-segmented mesh."""
     from ionization_b200 import configs, units as u
