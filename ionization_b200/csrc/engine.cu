@@ -585,15 +585,12 @@ int len_fold_prepare(ion_sim *s)
         const long long tasks = (long long)s->batch * (s->L / 2 - 1);
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
-        const int slots = 2 * prop.multiProcessorCount;
-        if (tasks >= 4LL * slots) {
-            CUDA_TRY(cudaFuncSetAttribute(ion::k_len_ens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ion::ens_smem_bytes()));
-            int per_sm = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ion::k_len_ens, ion::ENS_T, ion::ens_smem_bytes()));
-            if (per_sm >= 1) {
-                s->ens_ctas = per_sm * prop.multiProcessorCount;
-                s->ens_state = 1;
-            }
+        CUDA_TRY(cudaFuncSetAttribute(ion::k_len_ens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ion::ens_smem_bytes(ion::ENS_T)));
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ion::k_len_ens, ion::ENS_T, ion::ens_smem_bytes(ion::ENS_T)));
+        if (per_sm >= 1 && tasks >= 4LL * per_sm * prop.multiProcessorCount) {
+            s->ens_ctas = per_sm * prop.multiProcessorCount;
+            s->ens_state = 1;
         }
     }
     return ION_OK;
@@ -607,8 +604,8 @@ int launch_len_ens(ion_sim *s, const ion::UnitParams &p)
     cudaLaunchConfig_t cfg;
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)std::min<long long>(n_tasks, s->ens_ctas));
-    cfg.blockDim = dim3(ion::ENS_T);
-    cfg.dynamicSmemBytes = ion::ens_smem_bytes();
+    cfg.blockDim = dim3(s->T);
+    cfg.dynamicSmemBytes = ion::ens_smem_bytes(s->T);
     cfg.stream = s->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -17,10 +17,12 @@
 
 namespace ion {
 
-constexpr int ENS_T = 256;  // threads per CTA = threads per channel (r_points <= 1024)
+constexpr int ENS_T = 256;  // threads per CTA = threads per channel: r_points in (896, 1024].  Measured on smaller meshes (128- and
+                            // 64-thread channels, where k_unit already keeps 4 to 8 CTAs per SM in different phases): 40 % SLOWER
+                            // than one CTA per task (profiles/r01c_whatif_experiments.md), so the kernel is used for T = 256 only.
 
-// dynamic shared memory: scan scratch 256 cplx | LU factors 8*T cplx | tau*off 9*(T/2) doubles | psi stage 16*T cplx
-inline size_t ens_smem_bytes() { return (256 + 8 * (size_t)ENS_T + 16 * (size_t)ENS_T) * sizeof(cplx) + 9 * (size_t)(ENS_T / 2) * sizeof(double); }
+// dynamic shared memory: scan scratch 256 cplx | LU factors 8*T cplx | psi stage 16*T cplx | tau*off 9*(T/2) doubles
+inline size_t ens_smem_bytes(int T) { return (256 + 8 * (size_t)T + 16 * (size_t)T) * sizeof(cplx) + 9 * (size_t)(T / 2) * sizeof(double); }
 
 __global__ void __launch_bounds__(ENS_T, 2) k_len_ens(const UnitParams p, int n_pairs, long long n_tasks)
 {

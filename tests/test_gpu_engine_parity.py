@@ -503,7 +503,8 @@ def test_empty_call_and_step_by_step_equal_one_call(kind):
         assert rel_err(a.read_g()[0], b.read_g()[0]) < 1e-13
 
 
-def test_ensemble_persistent_prefetch_kernel_matches_one_cta_per_task(monkeypatch):
+@pytest.mark.parametrize("R,batch", [(1000, 400), (900, 420)])
+def test_ensemble_persistent_prefetch_kernel_matches_one_cta_per_task(monkeypatch, R, batch):
     """csrc/ensemble.cuh: scan ensembles with at least four waves of (pair, member) tasks run the folded length-gauge step in
     persistent CTAs with a cp.async prefetch pipeline.  Same arithmetic as k_unit<LEN_STEP>: compared with that path
     (ION_NO_ENS=1), with sparse observations in between, and member by member with the oracle."""
@@ -511,8 +512,8 @@ def test_ensemble_persistent_prefetch_kernel_matches_one_cta_per_task(monkeypatc
     from oracle import restate
 
     eng = _engine()
-    p = configs.spherical_harmonic_problem(r_bound=100 * u.bohr_radius, r_points=1000, l_bound=8, gauge="LEN", n_steps=14)
-    batch, n = 400, len(p["taus"])
+    p = configs.spherical_harmonic_problem(r_bound=0.1 * R * u.bohr_radius, r_points=R, l_bound=8, gauge="LEN", n_steps=14)
+    n = len(p["taus"])
     rng = np.random.default_rng(5)
     scale = rng.uniform(-3, 3, batch)
     fields = (np.asarray(p["fields"]) + 2e10)[:, None] * scale[None, :]
