@@ -533,3 +533,37 @@ def test_ensemble_persistent_prefetch_kernel_matches_one_cta_per_task(monkeypatc
         q["fields"] = fields[:, b]
         ref = restate.run_sh(q, store_every_step=False)
         assert rel_err(out["0"][0][b], ref["g"]) < TOL
+
+
+def _random_line_problem(kind, Z, n_steps, seed=0):
+    rng = np.random.default_rng(seed)
+    z = np.linspace(-1.0, 1.0, Z) * 0.05 * Z
+    dz = z[1] - z[0]
+    p = dict(kind=kind, Z=Z, z=z, delta_z=dz)
+    p["h_diag"] = rng.uniform(1.0, 4.0, Z) + 0.0j
+    p["h_off"] = -rng.uniform(0.4, 0.6, Z - 1)
+    p["w_z"] = z * 0.3
+    p["v_pref"] = 0.7
+    p["mask"] = np.cos(np.linspace(-1.2, 1.2, Z)) ** 0.125
+    g0 = rng.standard_normal(Z) + 1j * rng.standard_normal(Z)
+    p["g0"] = g0 / np.sqrt(np.sum(np.abs(g0) ** 2) * dz)
+    p["taus"] = np.full(n_steps, 0.05)
+    p["fields"] = rng.uniform(-1, 1, n_steps)
+    return p
+
+
+@pytest.mark.parametrize("kind", ["line_len_cn", "line_len_so", "line_vel_so"])
+@pytest.mark.parametrize("Z", [2, 3, 5, 33, 128, 129, 1000, 4097])
+def test_tiny_and_ragged_line_meshes_against_oracle(kind, Z):
+    """LineMesh edge cases (two points, odd sizes, one row past a CTA / a segment boundary) against the oracle"""
+    from oracle import restate
+
+    eng = _engine()
+    p = _random_line_problem(kind, Z, 6)
+    with eng.DeviceSimulation.from_problem(p, with_states=False) as sim:
+        sim.step(p["taus"], p["fields"])
+        g = sim.read_g()[0, 0]
+        norm = sim.observe(eng.nat.OBS_NORM)[0, 0]
+    ref = restate.run_line(p, store_every_step=False)
+    assert rel_err(g, ref["g"]) < TOL
+    assert abs(norm - ref["norm"][-1]) < TOL * max(1.0, ref["norm"][-1])
