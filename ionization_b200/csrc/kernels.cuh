@@ -731,14 +731,21 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
                 eangA = rot_angles<M>(cvec, kapA);
                 eangB = rot_angles<M>(cvec, kapB);
             }
-        } else {
-            pang = rpair_angles<M>(cvec, czp, kap0);
         }
+        // PROG_H2_CN_H2 follows k_slab, whose one CTA per SM holds the whole register file until it exits: no CTA of this kernel is
+        // resident early, so nothing placed before the wait overlaps the previous kernel.  Its trigonometry is therefore issued
+        // AFTER the psi loads, where it hides their latency (ION_H2_TRIG_FIRST restores the old order for A/B timing).
+#ifdef ION_H2_TRIG_FIRST
+        if (PROG == PROG_H2_CN_H2) pang = rpair_angles<M>(cvec, czp, kap0);
+#endif
         ION_CK(1);
         pdl_wait();
         ION_CK(2);
         load_rows<M>(A, base, T, t, true);
         load_rows<M>(B, base + chan, T, t, true);
+#ifndef ION_H2_TRIG_FIRST
+        if (PROG == PROG_H2_CN_H2) pang = rpair_angles<M>(cvec, czp, kap0);
+#endif
         if (PROG == PROG_LEN_STEP) {
             cplx Q[M];
             load_rows<M>(Q, base - chan, T, t, true);
