@@ -1026,7 +1026,14 @@ int ensure_observe_buffers(ion_sim *s, size_t n_records, uint32_t what)
     return ION_OK;
 }
 
-constexpr int64_t GRAPH_CHUNK = 64;
+// steps per captured graph: a chunk boundary costs a scalar refill (D2D copy) and a graph launch without overlap
+const int64_t GRAPH_CHUNK = [] {
+    if (const char *env = std::getenv("ION_GRAPH_CHUNK")) {
+        const long v = std::atol(env);
+        if (v >= 4 && v <= 4096) return (int64_t)v;
+    }
+    return (int64_t)64;
+}();
 
 // enqueue steps [n0, n0+len) reading scalars from `scal` (row n - n0 of it) and writing observations to `obs`
 int enqueue_steps(ion_sim *s, int64_t len, const double *scal, const uint8_t *pattern, bool pre_done_first, bool fuse_last,
