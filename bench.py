@@ -178,6 +178,9 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 for its workers; the reference arm is one process that may use every host thread
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 or os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     wl = build_workload(args.workload)
     problem, desc = wl[0], wl[1]
     from oracle import cport
@@ -375,7 +378,7 @@ def main():
     d2h = batch * L * R * 16 + batch * 8 * (1 + 2 * n_states)
 
     cpu_baseline = None
-    if rank == 0 and not args.no_cpu_baseline and str(problem["kind"]) != "sh_len_adi":  # the C port has no ADI
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and str(problem["kind"]) != "sh_len_adi":  # N = 1 only; the C port has no ADI
         try:
             v, n_cpu, dt_cpu, cores = cpu_reference_rate(problem, seconds_target=12.0)
             cpu_baseline = {"value": v, "unit": "updates/s", "cores": cores, "kind": "port",
