@@ -694,6 +694,8 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
             const size_t ch = (size_t)(l0 + (odd ? 1 : 0)) * T + 2 * pp;
             aP0 = ld_c(p.aggP + ch), aP1 = ld_c(p.aggP + ch + 1), aQ0 = ld_c(p.aggQ + ch), aQ1 = ld_c(p.aggQ + ch + 1);
         }
+        // LU factor of the row before the chunk (row 8pp - 1: the previous lane pair's last row, possibly another warp's)
+        const cplx wprev = pp > 0 ? ld_c(p.w + (size_t)(l0 + (odd ? 1 : 0)) * chan + 3 * (size_t)T + 2 * pp - 1) : c_zero();
         double cvec[M], czp = 0.0, kap0, kapA = 0.0, kapB = 0.0;
         if (PROG == PROG_ROT_CN_ROT || PROG == PROG_LEN_STEP) {
             load_vec<M>(cvec, p.vec, T, t, true);
@@ -766,12 +768,11 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         else h2_pair<M>(A, B, pang, false, tl, Tc, xs);  // (oe, oo)
         ION_CK(3);
         cp_async_wait_all();
-        __syncthreads();
+        __syncwarp();  // a thread reads factors staged by itself and by its lane-pair partner only (wprev comes from global memory)
         ION_CK(4);
         {
             cplx Z[8];
             pair_transpose_in(A, B, Z, odd);
-            const cplx wprev = tl >= 2 ? wsm[(size_t)7 * Tc + tl - 2] : c_zero();
             cn8(Z, wsm + tl, Tc, tosm + pp, wprev, P8, Q8, tl, Tc, sm_scan, p.short_scan);
             pair_transpose_out(Z, A, B, odd);
         }
