@@ -383,7 +383,8 @@ ION_DEVINL void rpair_layer_odd(cplx (&S)[M], cplx (&D)[M], const RPairAngles<M>
         nD0 = (t + 1 < T) ? xs[2 * T + t + 1] : c_zero();
         pDL = (t > 0) ? xs[3 * T + t - 1] : c_zero();
     }
-    __syncthreads();  // xs may be reused by the next layer
+    // no second barrier: every caller runs a CTA-wide barrier (the scans of a Crank-Nicolson solve) or ends the kernel before xs is
+    // written again -- one odd layer per h2_pair, and two h2_pair / line sweeps are always separated by a solve
     // interior odd pairs (k, k+1), k = 1, 3, ..., M-3
 #pragma unroll
     for (int k = 1; k + 1 < M; k += 2) {
