@@ -68,6 +68,29 @@ def ncu_traffic_warm(workload, kernel):
         return None
 
 
+def fp64_inst_per_point(workload, prof, n_prof, points):
+    """FP64 instructions (thread level: DFMA + DMUL + DADD) per grid point and time step: sum over the kernels of a step of
+    (instructions per launch from the committed ncu capture) x (launches per time step measured now) / points"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            entry = json.load(f)[workload]
+    except Exception:
+        entry = {}
+    total, used = 0.0, []
+    for k, (ms_k, n_k) in prof.items():
+        kname = {"slab": "k_slab", "adi_l": "k_adi_l", "len_ens": "k_len_ens"}.get(k, f"k_unit<{k}>")
+        e = entry.get(kname, {})
+        if "fp64_thread_inst" in e:
+            total += float(e["fp64_thread_inst"]) * (n_k / n_prof)
+            used.append(kname)
+        elif n_k / n_prof > 0.5:
+            return STATIC_FP64_PER_POINT.get(workload), "static count (DESIGN.md section 6); no ncu capture on file for " + kname
+    return (total / points if used else STATIC_FP64_PER_POINT.get(workload)), ("ncu capture (profiles/ncu_traffic.json): " + ", ".join(used)) if used else "static count (DESIGN.md section 6)"
+
+
+STATIC_FP64_PER_POINT = {"c3_vel": 166.0, "c3_len": 100.0, "c4_len_ensemble": 100.0}
+
+
 def build_workload(name):
     """-> (problem, description[, batch, fields[n_steps, batch]])"""
     from ionization_b200 import configs
@@ -174,6 +197,49 @@ def cpu_reference_rate(problem, seconds_target, min_steps=2, max_steps=400):
     return upd / dt, n, dt, cport.num_threads()
 
 
+def parity_prefix(sim, problem, batch, fields_all, n_check=32):
+    """Self-check outside the timed region: n_check consecutive time steps of THIS workload around the pulse maximum, from a
+    seeded state that populates every channel, on the schedule that is timed (CUDA graphs, fused kernels), compared with the
+    oracle's C restatement (pinned to the reference by tests/golden).  -> the "parity" object of the bench line."""
+    from oracle import cport
+
+    is_line = str(problem["kind"]).startswith("line")
+    n_all = len(problem["taus"])
+    f2 = np.asarray(fields_all).reshape(n_all, -1)
+    n = min(n_check, n_all)
+    start = int(min(max(0, int(np.argmax(np.abs(f2[:, -1]))) - n // 2), n_all - n))
+    taus = np.ascontiguousarray(problem["taus"][start : start + n])
+    fields = np.ascontiguousarray(f2[start : start + n] if f2.shape[1] > 1 else f2[start : start + n, 0])
+    rng = np.random.default_rng(11)
+    if is_line:
+        Z = int(problem["Z"])
+        z = np.asarray(problem["z"])
+        g0 = (rng.standard_normal(Z) + 1j * rng.standard_normal(Z)) * np.exp(-((z / z[-1]) ** 2) * 2)
+        g0 = (g0 / np.sqrt(np.sum(np.abs(g0) ** 2) * float(problem["delta_z"]))).reshape(1, Z)
+        shape = (batch, 1, Z)
+    else:
+        L, R = int(problem["L"]), int(problem["R"])
+        r = np.asarray(problem["r"])
+        g0 = (rng.standard_normal((L, R)) + 1j * rng.standard_normal((L, R))) * np.exp(-((r / r[-1]) ** 2) * 3)[None, :]
+        g0 *= np.exp(-np.arange(L) / (L / 4))[:, None]
+        g0 = g0 / np.sqrt(np.sum(np.abs(g0) ** 2) * float(problem["delta_r"]))
+        shape = (batch, L, R)
+    sim.write_g(np.ascontiguousarray(np.broadcast_to(g0, shape)))
+    sim.step(taus, fields)
+    g = sim.read_g()
+    members = sorted({0, batch // 2, batch - 1})
+    worst = 0.0
+    for b in members:
+        q = dict(problem)
+        q["g0"], q["taus"] = (g0[0] if is_line else g0), taus
+        q["fields"] = np.ascontiguousarray(fields[:, b]) if np.ndim(fields) == 2 else fields
+        ref = cport.line_steps(q) if is_line else cport.sh_steps(q)
+        got = g[b, 0] if is_line else g[b]
+        worst = max(worst, float(np.max(np.abs(got - ref)) / np.max(np.abs(ref))))
+    return {"max_rel_err": worst, "steps": n, "first_step": start, "members_checked": members, "against": "oracle C port (oracle/c/restate.c), seeded state over all channels",
+            "tolerance": 1e-10, "ok": bool(worst <= 1e-10)}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -224,6 +290,7 @@ def main():
     ap.add_argument("--workload", default="c3_vel")
     ap.add_argument("--time-steps", type=int, default=None, help="time steps per bench step (default: the workload's full pulse)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed self-check against the oracle")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -310,6 +377,14 @@ def main():
         step_resident()
     torch.cuda.synchronize()
 
+    # ---- self-check against the oracle (untimed; rank 0) ----
+    parity = None
+    if rank == 0 and not args.no_parity and str(problem["kind"]) != "sh_len_adi":  # the C port has no ADI (tests compare ADI with oracle/restate.py)
+        try:
+            parity = parity_prefix(sim, problem, batch, wl[3] if len(wl) > 3 else problem["fields"])
+        except Exception as exc:  # the checker is optional at bench time
+            parity = {"max_rel_err": None, "ok": False, "error": str(exc)}
+
     # ---- timed: device-resident ----
     sampler = ClockSampler(local_rank)
     barrier()
@@ -356,11 +431,10 @@ def main():
             dom = max(prof, key=lambda k: prof[k][0])
             dom_ms, dom_n = prof[dom]
             total_ms = sum(v[0] for v in prof.values())
-            # a k_unit launch streams the whole psi once; a k_resident launch advances psi by n_prof / launches whole time steps
-            steps_per_launch = n_prof / dom_n if dom == "resident" else 1.0
+            steps_per_launch = 1.0  # every k_unit / k_slab launch streams the whole psi once
             alg_bytes = BYTES_PER_UPDATE * L * R * batch * steps_per_launch
             achieved = alg_bytes / (dom_ms / dom_n * 1e-3) / 1e9
-            kname = {"resident": "k_resident", "slab": "k_slab", "adi_l": "k_adi_l", "len_ens": "k_len_ens"}.get(dom, f"k_unit<{dom}>")
+            kname = {"slab": "k_slab", "adi_l": "k_adi_l", "len_ens": "k_len_ens"}.get(dom, f"k_unit<{dom}>")
             roofline = {
                 "bound": "hbm", "kernel": kname, "time_steps_per_launch": steps_per_launch, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(args.workload, kname), "traffic_warm_l2": ncu_traffic_warm(args.workload, kname),
@@ -369,6 +443,22 @@ def main():
                 "kernels_us": {k: round(1e3 * v[0] / v[1], 3) for k, v in prof.items()},
                 "kernel_launches_per_time_step": {k: v[1] / n_prof for k, v in prof.items()},
             }
+            # second bound: the FP64 pipe.  Peak measured live (ion_fp64_peak: independent DFMA chains at
+            # full occupancy); FP64 instructions per grid point and time step from the committed ncu capture of this workload
+            # (profiles/ncu_traffic.json: sm__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on of one launch of each
+            # kernel of a step), else the static count stated in DESIGN.md.
+            try:
+                fma_per_s = engine.fp64_peak(local_rank)
+                ipp, ipp_src = fp64_inst_per_point(args.workload, prof, n_prof, L * R * batch)
+                step_s = ms * 1e-3 / args.steps / n_t
+                roofline["fp64"] = {
+                    "peak_measured_tflops": 2e-12 * fma_per_s, "peak_fma_per_s": fma_per_s, "inst_per_point": ipp, "inst_per_point_source": ipp_src,
+                    "achieved_inst_per_s": ipp * L * R * batch / step_s if ipp else None,
+                    "frac": (ipp * L * R * batch / step_s / fma_per_s) if ipp else None,
+                    "floor_us_per_time_step": (1e6 * ipp * L * R * batch / fma_per_s) if ipp else None,
+                }
+            except Exception as exc:
+                roofline["fp64"] = {"error": str(exc)}
 
     value = world * args.steps * updates_per_step / (ms * 1e-3)
     value_e2e = world * args.steps * updates_per_step / (ms_e2e * 1e-3)
@@ -394,7 +484,7 @@ def main():
             "config": {"workload": desc, "mesh_points": L * R, "time_steps_per_step": n_t, "sims_per_gpu": batch, "parallelism": f"ensemble x{world} (independent sims, no collective)",
                        "l2": "flushed between timed iterations (256 MB write); psi (16 B/pt) + CN factors (16 B/pt) are L2-resident within an iteration by design"},
             "hbm_roofline_frac_step": value / world * BYTES_PER_UPDATE / (peak * 1e9), "us_per_time_step": 1e3 * ms / args.steps / n_t,
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
             "e2e": {"value": value_e2e, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,
         }

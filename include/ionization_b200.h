@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ION_ABI_VERSION 1
+#define ION_ABI_VERSION 2
 
 /* status codes */
 #define ION_OK 0
@@ -200,6 +200,9 @@ int ion_num_kernel_kinds(void);
 const char *ion_kernel_name(int kind);
 int ion_sim_profile(ion_sim_t *sim, int64_t n_steps, const double *taus, const double *fields, double *ms,
                     int64_t *launches);
+/* Measured FP64 pipe peak of the device: thread-level double-precision FMAs per second of independent chains at full
+ * occupancy (x2 = FLOP/s).  The second bound bench.py reports next to the HBM roofline. */
+int ion_fp64_peak(int device, double *fma_per_second);
 
 #ifdef __cplusplus
 }

@@ -31,6 +31,7 @@ OBS_H0 = 32
 OBS_NORM_WITHIN = 64
 
 ION_ENODEVICE = -2
+ABI_VERSION = 2  # include/ionization_b200.h: ION_ABI_VERSION
 PEER_BLOB_BYTES = 96  # include/ionization_b200.h: ION_PEER_BLOB_BYTES
 
 _lib = None
@@ -79,6 +80,7 @@ SIGNATURES = {
     "ion_num_kernel_kinds": (_i32, []),
     "ion_kernel_name": (ctypes.c_char_p, [_i32]),
     "ion_sim_profile": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "ion_fp64_peak": (_i32, [_i32, _f64p]),
 }
 
 
@@ -106,6 +108,11 @@ def load():
             raise
         fn.restype = restype
         fn.argtypes = argtypes
+    if not os.environ.get("ION_LIB") and int(lib.ion_abi_version()) != ABI_VERSION:
+        raise exceptions.NativeLibraryMissing(
+            f"{LIB_PATH} implements C-ABI version {int(lib.ion_abi_version())}, this package binds version {ABI_VERSION}: "
+            "rebuild it with `python -m ionization_b200.build --force`"
+        )
     _lib = lib
     return lib
 

@@ -24,7 +24,6 @@
 
 #include "../../include/ionization_b200.h"
 #include "kernels.cuh"
-#include "resident.cuh"
 #include "slab.cuh"
 #include "adi.cuh"
 #include "ensemble.cuh"
@@ -60,7 +59,6 @@ enum KernelKind : int {
     KK_SWEEP_FLAT,
     KK_MASK,
     KK_OBSERVE,
-    KK_RESIDENT,
     KK_SLAB,
     KK_LEN_STEP,
     KK_HALO,
@@ -70,7 +68,7 @@ enum KernelKind : int {
 };
 const char *const kKernelNames[KK_COUNT] = {"rot",        "rot_cn_rot", "h2",        "h2_cn_h2", "cn",     "line_so_len",
                                             "line_so_vel", "line_cn",    "sweep_flat", "mask",    "observe",
-                                            "resident",    "slab",       "len_step",   "halo",
+                                            "slab",        "len_step",   "halo",
                                             "adi_l",       "len_ens"};
 
 template <typename T>
@@ -156,15 +154,12 @@ struct ion_sim {
     bool own_stream = false;
     bool use_graphs = true;
     bool use_pdl = true;
-    // on-chip resident kernel (resident.cuh): LL mailboxes between neighbouring CTAs, abort flag, exchange counter
-    bool use_resident = false;  // opt-in (ION_RESIDENT=1): slower than the streaming path on B200 as measured
-    int resident_state = 0;  // 0: not examined, 1: eligible, -1: not eligible
-    uint4 *halo = nullptr;
-    unsigned *abort_flag = nullptr;
-    unsigned ll_seq = 0;
-    int64_t resident_steps = 0;
-    bool resident_dirty = false;  // time steps advanced by the resident kernel (bench.py: algorithmic bytes per launch)
     bool capturing = false;
+    // per-call scalars: two pinned staging slots, so that ion_sim_step returns without waiting for the stream
+    double *scal_host[2] = {nullptr, nullptr};
+    size_t scal_host_cap[2] = {0, 0};
+    cudaEvent_t scal_ev[2] = {nullptr, nullptr};
+    int scal_slot = 0;
 
     // profiling
     bool profiling = false;
@@ -184,11 +179,13 @@ struct ion_sim {
         if (th) cudaFree(th);
         if (thd) cudaFree(thd);
         if (obs_chunk) cudaFree(obs_chunk);
-        if (halo) cudaFree(halo);
         for (void *q : peer_ipc_base)
             if (q) cudaIpcCloseMemHandle(q);
         if (hflags) cudaFree(hflags);
-        if (abort_flag) cudaFree(abort_flag);
+        for (int k = 0; k < 2; ++k) {
+            if (scal_host[k]) cudaFreeHost(scal_host[k]);
+            if (scal_ev[k]) cudaEventDestroy(scal_ev[k]);
+        }
         for (auto &g : graphs)
             if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
         for (auto e : ev) cudaEventDestroy(e);
@@ -856,116 +853,37 @@ int upload_scalars(ion_sim *s, int64_t n_steps, const double *taus, const double
         if (int rc = dev_alloc(&s->scal, need)) return rc;
         s->scal_cap = need;
     }
-    std::vector<double> h(need, 0.0);
+    // pinned staging, two slots: the copy is asynchronous and the host never waits for the stream here -- only for the
+    // copy that last used the slot it is about to refill (two calls ago)
+    const int k = s->scal_slot;
+    s->scal_slot ^= 1;
+    if (!s->scal_ev[k]) CUDA_TRY(cudaEventCreateWithFlags(&s->scal_ev[k], cudaEventDisableTiming));
+    else CUDA_TRY(cudaEventSynchronize(s->scal_ev[k]));
+    if (need > s->scal_host_cap[k]) {
+        if (s->scal_host[k]) cudaFreeHost(s->scal_host[k]);
+        s->scal_host[k] = nullptr;
+        s->scal_host_cap[k] = 0;
+        CUDA_TRY(cudaMallocHost((void **)&s->scal_host[k], need * sizeof(double)));
+        s->scal_host_cap[k] = need;
+    }
+    double *h = s->scal_host[k];
+    std::memset(h, 0, need * sizeof(double));
     for (int64_t n = 0; n < n_steps; ++n)
         for (int b = 0; b < s->batch; ++b) h[(size_t)(n + 1) * s->batch + b] = taus[n] * fields[(size_t)n * s->batch + b];
-    CUDA_TRY(cudaMemcpyAsync(s->scal, h.data(), need * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    CUDA_TRY(cudaStreamSynchronize(s->stream));  // h goes out of scope
+    CUDA_TRY(cudaMemcpyAsync(s->scal, h, need * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaEventRecord(s->scal_ev[k], s->stream));
     return ION_OK;
 }
 
-// ---------------------------------------------------------------------------------------------
-// on-chip resident path (resident.cuh)
-// ---------------------------------------------------------------------------------------------
-size_t resident_smem_bytes(const ion_sim *s, bool vel)
+// after a synchronisation point: did a peer-memory halo exchange of this l-block shard time out?  A shard that missed a
+// hand-shake has kept stepping with stale ghost channels, so the wavefunction of the handle is invalid from then on.
+int check_abort(ion_sim *s)
 {
-    const size_t T = (size_t)s->T, TH = T / 2;
-    size_t n = (16 * T + 4 * T + 128) * sizeof(cplx) + (9 * TH + (TH & 1)) * sizeof(double);
-    if (vel) n += 4 * T * sizeof(cplx);
-    return n;
-}
-
-const void *resident_kernel(const ion_sim *s)
-{
-    return s->program == ION_SH_VEL_SO ? (const void *)ion::k_resident<1> : (const void *)ion::k_resident<0>;
-}
-
-// Decide once per handle whether the simulation fits on chip: split-operator SphericalHarmonic program, even l_bound,
-// unsharded, <= 2048 radial rows, and ceil(L/4) x batch CTAs all co-resident (cooperative launch).
-int resident_prepare(ion_sim *s)
-{
-    if (s->resident_state != 0) return ION_OK;
-    s->resident_state = -1;
-    if (!s->use_resident) return ION_OK;
-    if (s->program != ION_SH_LEN_SO && s->program != ION_SH_VEL_SO) return ION_OK;
-    if ((s->L_total % 2) != 0 || s->L_own != s->L_total || s->M != 4 || s->S != 1 || s->T > 512) return ION_OK;
-    const bool vel = s->program == ION_SH_VEL_SO;
-    int coop = 0, sms = 0;
-    CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s->device));
-    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
-    if (!coop) return ION_OK;
-    const size_t smem = resident_smem_bytes(s, vel);
-    const void *fn = resident_kernel(s);
-    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        cudaGetLastError();
-        return ION_OK;
-    }
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, s->T, smem));
-    const int nblk = (s->L + 3) / 4;
-    if ((long long)nblk * s->batch > (long long)per_sm * sms) return ION_OK;
-    const size_t n_box = (size_t)s->batch * nblk * 2 * 2 * 8 * s->T;
-    if (int rc = dev_alloc(&s->halo, n_box)) return rc;
-    CUDA_TRY(cudaMemsetAsync(s->halo, 0, n_box * sizeof(uint4), s->stream));
-    if (int rc = dev_alloc(&s->abort_flag, 1)) return rc;
-    CUDA_TRY(cudaMemsetAsync(s->abort_flag, 0, sizeof(unsigned), s->stream));
-    s->ll_seq = 0;
-    s->resident_state = 1;
-    return ION_OK;
-}
-
-int launch_resident(ion_sim *s, const double *scal_dev, int64_t n_steps)
-{
-    const bool vel = s->program == ION_SH_VEL_SO;
-    const int nblk = (s->L + 3) / 4;
-    const unsigned per_step = vel ? 4u : 2u;
-    if ((uint64_t)s->ll_seq + (uint64_t)n_steps * per_step > 0xF0000000ull) {  // sequence numbers about to wrap: start over
-        const size_t n_box = (size_t)s->batch * nblk * 2 * 2 * 8 * s->T;
-        CUDA_TRY(cudaMemsetAsync(s->halo, 0, n_box * sizeof(uint4), s->stream));
-        s->ll_seq = 0;
-    }
-    ion::ResidentParams p;
-    std::memset(&p, 0, sizeof(p));
-    p.psi = s->psi;
-    p.w = s->w;
-    p.toff = s->toff;
-    p.vec = s->vec;
-    p.zvec = s->zvec;
-    p.zprev = s->zprev;
-    p.mask = s->mask;
-    p.cl = s->cl;
-    p.cl2 = s->cl2;
-    p.scal = scal_dev;
-    p.halo = s->halo;
-    p.abort_flag = s->abort_flag;
-    p.n_steps = n_steps;
-    p.spin_limit = 4000000000ll;  // ~2 s of SM clock
-    p.L = s->L;
-    p.T = s->T;
-    p.batch = s->batch;
-    p.short_scan = s->short_scan;
-    p.seq_base = s->ll_seq;
-    if (const char *env = std::getenv("ION_RES_DBG")) p.dbg = std::atoi(env);
-    s->ll_seq += (unsigned)(n_steps * per_step);
-    void *args[] = {&p};
-    prof_begin(s, KK_RESIDENT);
-    CUDA_TRY(cudaLaunchCooperativeKernel(resident_kernel(s), dim3(nblk, s->batch), dim3(s->T), args, resident_smem_bytes(s, vel), s->stream));
-    prof_end(s);
-    s->launch_count++;
-    s->resident_steps += n_steps;
-    s->resident_dirty = true;
-    return ION_OK;
-}
-
-// after a synchronisation point: did an exchange of the resident kernel time out?
-int check_resident_abort(ion_sim *s)
-{
-    if (!s->resident_dirty || !s->abort_flag) return ION_OK;
-    unsigned flag = 0;
-    CUDA_TRY(cudaMemcpyAsync(&flag, s->abort_flag, sizeof(flag), cudaMemcpyDeviceToHost, s->stream));
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
-    s->resident_dirty = false;
-    if (flag) return fail(ION_ECUDA, "resident kernel: a boundary-channel exchange between CTAs timed out; the wavefunction of this handle is invalid");
+    if (!s->peers_attached || !s->hflags) return ION_OK;
+    unsigned long long flag = 0;
+    CUDA_TRY(cudaMemcpy(&flag, s->hflags + ion::HF_ABORT, sizeof(flag), cudaMemcpyDeviceToHost));
+    if (flag)
+        return fail(ION_ECUDA, "l-block shard: a peer-memory halo exchange timed out (a neighbour never arrived); the wavefunction of this handle is invalid");
     return ION_OK;
 }
 
@@ -1084,26 +1002,11 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
     for (int64_t n = 1; n < n_steps; ++n)
         if (std::fabs(taus[n] - taus[0]) > 1e-9 * std::fabs(taus[0])) uniform_tau = false;
 
-    if (int rc = resident_prepare(s)) return rc;
     if (int rc = slab_prepare(s)) return rc;
     if (int rc = len_fold_prepare(s)) return rc;
     if (s->S > 1 || s->program == ION_SH_LEN_ADI)
         if (int rc = ensure_second_buffer(s)) return rc;  // segmented kernels run out of place
-    if (s->resident_state == 1 && uniform_tau) {
-        // on-chip resident kernel: one persistent launch per stretch between observations
-        if (int rc = ensure_factor(s, taus[0])) return rc;
-        int64_t n0 = 0, k_obs = 0;
-        for (int64_t n = 0; n < n_steps; ++n) {
-            const bool obs = observe_mask && observe_mask[n];
-            if (!obs && n + 1 < n_steps) continue;
-            if (int rc = launch_resident(s, s->scal + (size_t)(n0 + 1) * s->batch, n + 1 - n0)) return rc;
-            n0 = n + 1;
-            if (obs) {
-                if (int rc = launch_observe(s, what, s->obs_out + (size_t)k_obs * rec)) return rc;
-                ++k_obs;
-            }
-        }
-    } else if (!(s->use_graphs && uniform_tau && !s->profiling && s->stream != 0 && n_steps >= 4)) {
+    if (!(s->use_graphs && uniform_tau && !s->profiling && s->stream != 0 && n_steps >= 4)) {
         bool pre_done = false;
         int64_t k_obs = 0;
         for (int64_t n = 0; n < n_steps; ++n) {
@@ -1190,7 +1093,7 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
     if (n_obs) {
         CUDA_TRY(cudaMemcpyAsync(out, s->obs_out, (size_t)n_obs * rec * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
-        if (int rc = check_resident_abort(s)) return rc;
+        if (int rc = check_abort(s)) return rc;
     }
     return ION_OK;
 }
@@ -1326,8 +1229,6 @@ int ion_sim_create_sharded(int program, int64_t L_total, int64_t l_begin, int64_
     else s->stream = 0;
     if (const char *env = std::getenv("ION_NO_GRAPHS")) s->use_graphs = !(env[0] == '1');
     if (const char *env = std::getenv("ION_NO_PDL")) s->use_pdl = !(env[0] == '1');
-    if (const char *env = std::getenv("ION_RESIDENT")) s->use_resident = (env[0] == '1');
-    if (const char *env = std::getenv("ION_NO_RESIDENT")) s->use_resident = s->use_resident && !(env[0] == '1');
     if (const char *env = std::getenv("ION_NO_SLAB")) s->use_slab = !(env[0] == '1');
     if (const char *env = std::getenv("ION_NO_LEN_FOLD")) s->use_len_fold = !(env[0] == '1');
     if (const char *env = std::getenv("ION_NO_ENS")) s->use_ens = !(env[0] == '1');
@@ -1527,7 +1428,7 @@ int ion_sim_read_g(ion_sim_t *s, void *g)
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(g, s->io_stage, n * s->R * sizeof(cplx), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    return check_resident_abort(s);
+    return check_abort(s);
 }
 
 int ion_sim_step(ion_sim_t *s, int64_t n_steps, const double *taus, const double *fields)
@@ -1559,7 +1460,7 @@ int ion_sim_observe(ion_sim_t *s, uint32_t what, double *out)
     const size_t rec = (size_t)ion_sim_observation_size(s, what) * s->batch;
     CUDA_TRY(cudaMemcpyAsync(out, s->obs_out, rec * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    return check_resident_abort(s);
+    return check_abort(s);
 }
 
 int ion_sim_run(ion_sim_t *s, int64_t n_steps, const double *taus, const double *fields, const uint8_t *observe_mask,
@@ -1569,7 +1470,7 @@ int ion_sim_run(ion_sim_t *s, int64_t n_steps, const double *taus, const double 
     int rc = run_impl(s, n_steps, taus, fields, observe_mask, what, out);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    return check_resident_abort(s);
+    return check_abort(s);
 }
 
 int ion_sim_synchronize(ion_sim_t *s)
@@ -1577,7 +1478,7 @@ int ion_sim_synchronize(ion_sim_t *s)
     if (!s) return fail(ION_EINVAL, "sim is NULL");
     CUDA_TRY(cudaSetDevice(s->device));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    return check_resident_abort(s);
+    return check_abort(s);
 }
 
 int ion_sim_halo_buffer(ion_sim_t *s, int which, void **device_ptr, int64_t *n_bytes)
@@ -1778,6 +1679,59 @@ int ion_sim_device_psi(ion_sim_t *s, void **device_ptr, int64_t *n_bytes)
 }
 
 int64_t ion_sim_launch_count(ion_sim_t *s) { return s ? s->launch_count : 0; }
+
+// FP64 pipe peak, measured: independent DFMA chains at full occupancy (the second bound of the roofline: the hot path is
+// complex128 arithmetic, no contraction, so the tensor cores do not apply and the FP64 FMA pipe is the compute ceiling)
+namespace {
+__global__ void __launch_bounds__(512) k_fp64_peak(double *out, int iters)
+{
+    double a = threadIdx.x * 1e-3, b = 1.0000001, c = 1e-9, d = a + 1, e = a + 2, f = a + 3, g = a + 4, h = a + 5, i2 = a + 6, j = a + 7;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        a = fma(a, b, c);
+        d = fma(d, b, c);
+        e = fma(e, b, c);
+        f = fma(f, b, c);
+        g = fma(g, b, c);
+        h = fma(h, b, c);
+        i2 = fma(i2, b, c);
+        j = fma(j, b, c);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a + d + e + f + g + h + i2 + j;
+}
+}  // namespace
+
+int ion_fp64_peak(int device, double *fma_per_second)
+{
+    if (!fma_per_second) return fail(ION_EINVAL, "NULL argument");
+    if (ion_device_count() <= device || device < 0) return fail(ION_ENODEVICE, "no CUDA device " + std::to_string(device));
+    CUDA_TRY(cudaSetDevice(device));
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int grid = sms * 4, block = 512, iters = 8192;
+    double *out = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&out, (size_t)grid * block * sizeof(double)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        k_fp64_peak<<<grid, block>>>(out, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    if (e != cudaSuccess) return fail(ION_ECUDA, cudaGetErrorString(e));
+    *fma_per_second = (double)grid * block * iters * 8.0 / (best * 1e-3);
+    return ION_OK;
+}
 int ion_num_kernel_kinds(void) { return KK_COUNT; }
 const char *ion_kernel_name(int kind) { return (kind >= 0 && kind < KK_COUNT) ? kKernelNames[kind] : ""; }
 

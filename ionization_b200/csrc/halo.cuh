@@ -87,6 +87,10 @@ __global__ void __launch_bounds__(256) k_halo_exchange(const HaloParams p)
                 st_release_sys(p.peer_flags[side] + HF_ARRIVE + other, k);
             }
             ok_sm = halo_spin(flags + HF_ARRIVE + side, k, flags, p.spin_limit) ? 1 : 0;
+            if (!ok_sm) {  // tell both neighbours: they must not keep stepping with a ghost channel that never arrived here
+                for (int q = 0; q < 2; ++q)
+                    if (p.peer_flags[q]) st_release_sys(p.peer_flags[q] + HF_ABORT, 1ull);
+            }
         }
         __syncthreads();
         if (ok_sm) {

@@ -26,6 +26,13 @@ def device_count() -> int:
     return int(nat.load().ion_device_count())
 
 
+def fp64_peak(device: int = 0) -> float:
+    """measured FP64 pipe peak of the device in thread-level FMAs per second (x2 = FLOP/s)"""
+    v = ctypes.c_double(0.0)
+    nat.check(nat.load().ion_fp64_peak(int(device), ctypes.byref(v)), "ion_fp64_peak")
+    return float(v.value)
+
+
 def tdma(matrix, d, device: int = 0):
     """Drop-in for ``ionization.cy.tdma(matrix, d)`` (cy.pyx:9-50): x = matrix^-1 d, no pivoting.
 

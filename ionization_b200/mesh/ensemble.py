@@ -31,6 +31,17 @@ def _compatible(a, b):
         return "mask differs"
     if a.initial_state != b.initial_state:
         return "initial_state differs"
+    # the members share ONE Hamiltonian, one basis of test states and one observation record layout on the device
+    if repr(a.internal_potential) != repr(b.internal_potential):
+        return "internal_potential differs"
+    for k in ("use_numeric_eigenstates", "numeric_eigenstate_max_energy", "numeric_eigenstate_max_angular_momentum", "number_of_numeric_eigenstates",
+              "analytic_eigenstate_type"):
+        if getattr(a, k, None) != getattr(b, k, None):
+            return f"{k} differs"
+    if a.datastore_types != b.datastore_types:
+        return "datastore types differ"
+    if [repr(s) for s in a.test_states] != [repr(s) for s in b.test_states] and not getattr(a, "use_numeric_eigenstates", False):
+        return "test_states differ"
     return None
 
 
@@ -42,6 +53,7 @@ class MeshEnsemble:
         specs = list(specs)
         if not specs:
             raise exceptions.EngineError("empty ensemble")
+        # compared BEFORE the first member's to_sim(), which may replace its states by the numeric basis
         for s in specs[1:]:
             why = _compatible(specs[0], s)
             if why:
@@ -57,7 +69,16 @@ class MeshEnsemble:
     @staticmethod
     def _clone_member(first, spec):
         from .. import coefficients as C
+        from .. import potentials
 
+        # every member gets the corrections MeshSimulation.__init__ applies to its own pulse (mesh/sims.py:53-75; scans
+        # DC-correct by default, ionization_scans/scan_utils.py:517)
+        if spec.electric_potential_dc_correction:
+            spec.electric_potential = potentials.DC_correct_electric_potential(spec.electric_potential, first.times)
+        if spec.electric_potential_fluence_correction:
+            spec.electric_potential = potentials.FluenceCorrector(
+                electric_potential=spec.electric_potential, times=first.times, target_fluence=list(spec.electric_potential)[0].fluence
+            )
         sim = copy.copy(first)
         sim.uuid = uuid.uuid4()
         sim.name = spec.name

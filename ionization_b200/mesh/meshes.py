@@ -103,8 +103,13 @@ class QuantumMesh:
         """device reductions of the current wavefunction -> dict"""
         eng = self.engine
         self._upload_if_needed()
-        rec = eng.observe(what)[0]
-        return self.sim._split_record(rec, what)
+        line_z = isinstance(self, LineMesh) and bool(what & nat.OBS_Z)
+        if line_z:  # on a line <z> = sum z |g|^2 is the engine's "r" observable (there is no l coupling to evaluate)
+            what = (what & ~nat.OBS_Z) | nat.OBS_R
+        rec = self.sim._split_record(eng.observe(what)[0], what)
+        if line_z:
+            rec["z"] = rec["r"]
+        return rec
 
     def inner_product(self, a=None, b=None):
         """meshes.py:195-200; (state, None) for a registered test state is a device reduction"""

@@ -377,10 +377,10 @@ class MeshSimulation(_Beet):
             e, a = self._host_fields()
             record["electric_field_amplitude"] = e[time_index]
             record["vector_potential_amplitude"] = a[time_index]
+        if self.mesh.__class__ is meshes.LineMesh and "z" not in record and "r" in record:
+            record["z"] = record["r"]  # on a line <z> is the engine's "r" observable (see _obs_mask); total energy needs it
         if data_mod.TotalEnergyExpectationValue in self.datastores_by_type:
             record["total_energy"] = self._total_energy(record, time_index)
-        if self.mesh.__class__ is meshes.LineMesh and "z" not in record and "r" in record:
-            record["z"] = record["r"]
         return record
 
     def store_data(self, record=None):

@@ -199,11 +199,20 @@ class ShardedSimulation:
         taus = np.atleast_1d(taus)
         fields = np.atleast_1d(fields)
         ctx = torch.cuda.stream(self.stream) if self.stream is not None else _NullCtx()
+        # NCCL p2p synchronises with torch's CURRENT stream.  When the engine runs on a torch stream (the default), that
+        # stream is made current and everything is stream-ordered; when it runs on its own private stream the exchange is
+        # fenced explicitly on both sides (the phase kernels must have finished before the boundary channels are sent, and the
+        # received ghosts must have landed before the next phase reads them).
+        fence = exchanger is not None and self.stream is None
         with ctx:
             for tau, f in zip(taus, fields):
                 for ph in range(self.n_phases):
                     if exchanger is not None and ph in self.halo_phases:
+                        if fence:
+                            self.engine.synchronize()
                         exchanger.exchange()
+                        if fence:
+                            torch.cuda.current_stream(self.device).synchronize()
                     self.engine.step_phase(ph, float(tau), float(f))
 
     # ---- observables ---------------------------------------------------------------------------

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_library_reports_abi_version_and_fails_cleanly_without_device():
     lib = _native.load()
-    assert lib.ion_abi_version() == 1
+    assert lib.ion_abi_version() == _native.ABI_VERSION
     if lib.ion_device_count() == 0:
         h = ctypes.c_void_p()
         rc = lib.ion_sim_create(0, 4, 16, 1, 0, ctypes.byref(h))

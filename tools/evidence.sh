@@ -3,7 +3,7 @@
 tag=$1
 o=gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 400 --csv --log-file $o/${tag}_launches.csv python bench.py --steps 1 --warmup 1 --time-steps 200 --no-cpu-baseline > $o/${tag}_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_slab|k_unit" -s 24 -c 2 -f -o $o/${tag}_prof python bench.py --steps 1 --warmup 1 --time-steps 20 --no-cpu-baseline > $o/${tag}_prof.log 2>&1
+ncu --set full --metrics smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum --clock-control none --import-source on -k regex:"k_slab|k_unit" -s 24 -c 2 -f -o $o/${tag}_prof python bench.py --steps 1 --warmup 1 --time-steps 20 --no-cpu-baseline > $o/${tag}_prof.log 2>&1
 ncu --set full --cache-control none --clock-control none --import-source on -k regex:"k_slab|k_unit" -s 24 -c 2 -f -o $o/${tag}_prof_warm python bench.py --steps 1 --warmup 1 --time-steps 20 --no-cpu-baseline > $o/${tag}_prof_warm.log 2>&1
 ncu --set full --clock-control none -k regex:k_unit -s 12 -c 1 -f -o $o/${tag}_prof_c4 python bench.py --workload c4_len_ensemble --steps 1 --warmup 1 --time-steps 6 --no-cpu-baseline > $o/${tag}_prof_c4.log 2>&1
 ncu --set full --clock-control none -k regex:"k_adi_l|k_unit" -s 12 -c 2 -f -o $o/${tag}_prof_adi python bench.py --workload c3_adi --steps 1 --warmup 1 --time-steps 10 --no-cpu-baseline > $o/${tag}_prof_adi.log 2>&1

@@ -2,6 +2,7 @@
 """DRAM traffic per launch of every kernel in an `ncu --set full` report -> profiles/ncu_traffic.json (read by bench.py's
 roofline.traffic).  usage: tools/ncu_traffic.py WORKLOAD report.ncu-rep [profiles/ncu_traffic.json]"""
 import csv
+import re
 import json
 import os
 import subprocess
@@ -23,11 +24,15 @@ def short(name):
 rows = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout.splitlines()))
 hdr, units = rows[0], rows[1]
 kn, rd, wr, du = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+# FP64 instructions executed (thread level): add `--metrics smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,
+# smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum` to the capture
+fp = [i for i, h in enumerate(hdr) if re.search(r"sass_thread_inst_executed_op_d(fma|mul|add)_pred_on\.sum$", h)]
 acc = {}
 for r in rows[2:]:
     k = short(r[kn])
-    a = acc.setdefault(k, [0, 0.0, 0.0, 0.0])
+    a = acc.setdefault(k, [0, 0.0, 0.0, 0.0, 0.0])
     a[0] += 1
+    a[4] += sum(float(r[i].replace(",", "")) for i in fp)
     a[1] += float(r[rd].replace(",", "")) * UNIT[units[rd]]
     a[2] += float(r[wr].replace(",", "")) * UNIT[units[wr]]
     a[3] += float(r[du].replace(",", ""))
@@ -35,6 +40,6 @@ try:
     data = json.load(open(out_path))
 except Exception:
     data = {}
-data[workload] = {k: {"dram_bytes_read": a[1] / a[0], "dram_bytes_write": a[2] / a[0], "launches_captured": a[0], "source": os.path.basename(rep) + " (ncu --set full, caches flushed between replays)"} for k, a in acc.items()}
+data[workload] = {k: {"dram_bytes_read": a[1] / a[0], "dram_bytes_write": a[2] / a[0], "launches_captured": a[0], **({"fp64_thread_inst": a[4] / a[0]} if fp else {}), "source": os.path.basename(rep) + " (ncu --set full, caches flushed between replays)"} for k, a in acc.items()}
 json.dump(data, open(out_path, "w"), indent=1, sort_keys=True)
 print(json.dumps(data[workload], indent=1))
