@@ -135,6 +135,7 @@ struct ion_sim {
     double *partial = nullptr, *ip_out = nullptr, *obs_out = nullptr;
     size_t obs_cap = 0;
 
+    double vec_dv = 0.0;  // length gauge: increment of the coupling vector per radial row when it is linear to rounding, else 0
     bool have_h = false, have_coupling = false;
     double factored_tau = 0.0;
     bool factored = false;
@@ -341,6 +342,7 @@ ion::UnitParams base_params(ion_sim *s)
     p.H = s->H;
     p.l_begin = s->l_begin;
     p.short_scan = s->short_scan;
+    p.vec_dv = s->vec_dv;
     p.unit0 = 0;
     p.unit_stride = 1;
     return p;
@@ -631,14 +633,19 @@ int slab_prepare(ion_sim *s)
         const int v = std::atoi(env);
         if (v == 4 || v == 8 || v == 16 || v == 32) G = v;
     }
+    int nt_cap = 512;  // threads per CTA: 512 -> one CTA per SM (128 registers); <= 288 -> two co-resident CTAs per SM
+    if (const char *env = std::getenv("ION_SLAB_NT")) {
+        const int v = std::atoi(env);
+        if (v >= 64 && v <= 512) nt_cap = v;
+    }
     const int nQ = (s->L + 3) / 4;
     int chunks = 1, Qc = nQ, loaded = nQ;
     for (;; ++chunks) {
         Qc = (nQ + chunks - 1) / chunks;
         loaded = Qc + (chunks == 1 ? 0 : (chunks == 2 ? 1 : 2));
-        if (G * loaded <= 512 || Qc == 1) break;
+        if (G * loaded <= nt_cap || Qc == 1) break;
     }
-    if (G * loaded > 512) return ION_OK;
+    if (G * loaded > nt_cap) return ION_OK;
     chunks = (nQ + Qc - 1) / Qc;
     const int W = 4 * G - 4;
     s->slab_G = G;
@@ -649,6 +656,7 @@ int slab_prepare(ion_sim *s)
     s->slab_threads = (G * loaded + 31) / 32 * 32;
     if (int rc = ensure_second_buffer(s)) return rc;
     CUDA_TRY(cudaFuncSetAttribute(ion::k_slab<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 512 * (int)sizeof(cplx)));
+    CUDA_TRY(cudaFuncSetAttribute(ion::k_slab<288>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 288 * (int)sizeof(cplx)));
     s->slab_state = 1;
     return ION_OK;
 }
@@ -685,7 +693,8 @@ int launch_slab(ion_sim *s, const double *sa, const double *sb)
     cfg.attrs = attr;
     cfg.numAttrs = s->use_pdl ? 1 : 0;
     prof_begin(s, KK_SLAB);
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_slab<512>, p));
+    if (s->slab_threads <= 288) CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_slab<288>, p));
+    else CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_slab<512>, p));
     prof_end(s);
     s->launch_count++;
     std::swap(s->psi, s->psi2);
@@ -1297,6 +1306,18 @@ int ion_sim_set_len_coupling(ion_sim_t *s, const double *c_l, const double *x_j)
     if (int rc = upload_plain(s, c_l, (size_t)s->L_total - 1, &s->cl)) return rc;
     if (int rc = upload_plain(s, c_l, (size_t)s->L_total - 1, &s->cl_z)) return rc;
     if (int rc = upload_permuted(s, x_j, s->R, &s->vec, nullptr)) return rc;
+    // x_j = -q r_j on the reference's uniform radial grid (meshes.py:1009-1011) is linear in j: the kernels then get the
+    // rotation angles of a thread's consecutive rows by angle addition.  Verified here, to rounding, for whatever the caller passed.
+    s->vec_dv = 0.0;
+    if (s->R >= 3 && s->M == 4 && !std::getenv("ION_NO_LINEAR_ANGLES")) {
+        const double dv = (x_j[s->R - 1] - x_j[0]) / (double)(s->R - 1);
+        double dev = 0.0, mx = 0.0;
+        for (int64_t j = 0; j < s->R; ++j) {
+            dev = std::max(dev, std::fabs(x_j[j] - (x_j[0] + (double)j * dv)));
+            mx = std::max(mx, std::fabs(x_j[j]));
+        }
+        if (dv != 0.0 && dev <= 8.0 * 2.220446049250313e-16 * mx) s->vec_dv = dv;
+    }
     s->have_coupling = true;
     return ION_OK;
 }

@@ -86,11 +86,11 @@ __global__ void __launch_bounds__(ENS_T, 2) k_len_ens(const UnitParams p, int n_
         const double sa = p.scal_a ? p.scal_a[b] : 0.0, sb = p.scal_b ? p.scal_b[b] : 0.0;
         double vec[M];  // re-read per task (L1): keeping it across tasks costs registers the solve needs
         load_vec<M>(vec, p.vec, T, tl, true);
-        const RotAngles<M> rang = rot_angles<M>(vec, sa * p.cl[l0]);
+        const RotAngles<M> rang = rot_angles_auto<M>(vec, p.vec_dv, sa * p.cl[l0]);
         cplx A[M], B[M];
         {
-            const RotAngles<M> eangA = rot_angles<M>(vec, (sa + sb) * p.cl[l0 - 1]);
-            const RotAngles<M> eangB = rot_angles<M>(vec, (sa + sb) * p.cl[l0 + 1]);
+            const RotAngles<M> eangA = rot_angles_auto<M>(vec, p.vec_dv, (sa + sb) * p.cl[l0 - 1]);
+            const RotAngles<M> eangB = rot_angles_auto<M>(vec, p.vec_dv, (sa + sb) * p.cl[l0 + 1]);
             // ---- psi of this task: staged by this very thread during the previous task ----
             asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but F(task) has landed
             cplx QA[M], QB[M];

@@ -52,6 +52,7 @@ struct UnitParams {
     int parity;              // parity (in GLOBAL l) of the lower channel of a pair
     int flags;
     int short_scan;          // reach of the cross-warp inflow of the CN scans in warps (0: full scan; see common.cuh)
+    double vec_dv;           // != 0: vec is linear in the row index with this increment per row (length gauge on the uniform radial grid)
     int unit0, unit_stride;  // unit of CTA x = unit0 + x * unit_stride (0, 1: all units; the ensemble kernel leaves the single channels to k_unit)
 };
 
@@ -116,6 +117,32 @@ ION_DEVINL RotAngles<M> rot_angles(const double (&vec)[M], double sc)
     for (int k = 0; k < M; ++k) th[k] = sc * vec[k];
     fast_sincos_n<M>(th, a.s, a.c);
     return a;
+}
+// The same for a coupling vector that is LINEAR in the row index, vec[i] = vec[0] + i * dv (the length gauge: x_j = -q r_j on
+// the uniform radial grid): theta_k = sc * (v0 + k dv), so one sincos for the thread's first row, one for the increment
+// (the same for every thread of the pair) and M - 1 complex multiplications replace M sincos evaluations.  Rounding: each
+// multiplication adds <= 2 ulp to cos/sin, i.e. < 1e-15 absolute after M - 1 = 3 of them.
+template <int M>
+ION_DEVINL RotAngles<M> rot_angles_linear(double v0, double dv, double sc)
+{
+    RotAngles<M> a;
+    const double th[2] = {sc * v0, sc * dv};
+    double sn[2], cs[2];
+    fast_sincos_n<2>(th, sn, cs);
+    a.c[0] = cs[0];
+    a.s[0] = sn[0];
+#pragma unroll
+    for (int k = 1; k < M; ++k) {
+        a.c[k] = fma(a.c[k - 1], cs[1], -a.s[k - 1] * sn[1]);
+        a.s[k] = fma(a.s[k - 1], cs[1], a.c[k - 1] * sn[1]);
+    }
+    return a;
+}
+// vec_dv != 0: the host verified (ion_sim_set_len_coupling) that the coupling vector is linear in the row index to rounding
+template <int M>
+ION_DEVINL RotAngles<M> rot_angles_auto(const double (&vec)[M], double vec_dv, double sc)
+{
+    return vec_dv != 0.0 ? rot_angles_linear<M>(vec[0], vec_dv, sc) : rot_angles<M>(vec, sc);
 }
 template <int M, bool REAL>
 ION_DEVINL void rotate_pair(cplx (&A)[M], cplx (&B)[M], const RotAngles<M> &ang)
@@ -579,8 +606,11 @@ ION_DEVINL void line_cn_factors(CnFactors<M> &f, const cplx (&D)[M], const doubl
 // because the LU multipliers decay geometrically -- the host verifies (k_scan_bound) that their product over any 32
 // threads is below 1e-30 before it allows S > 1.  Halo results are discarded; only interior threads store.
 template <int M, int PROG, int TMAX, bool SEG>
+#ifndef ION_PAIR_MINB
+#define ION_PAIR_MINB 1
+#endif
 __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) && TMAX <= 512) ? (M <= 4 ? 1024 / TMAX : 2)
-                                                                                            : ((M <= 4 && TMAX <= 256) ? 2 : 1))
+                                                                                            : ((M <= 4 && TMAX <= 256) ? 2 : (TMAX == 512 && M == 4 ? ION_PAIR_MINB : 1)))
     k_unit(const UnitParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -729,10 +759,10 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         RotAngles<M> rang, eangA, eangB;
         RPairAngles<M> pang;
         if (PROG == PROG_ROT_CN_ROT || PROG == PROG_LEN_STEP) {
-            rang = rot_angles<M>(cvec, kap0);
+            rang = rot_angles_auto<M>(cvec, p.vec_dv, kap0);
             if (PROG == PROG_LEN_STEP) {
-                eangA = rot_angles<M>(cvec, kapA);
-                eangB = rot_angles<M>(cvec, kapB);
+                eangA = rot_angles_auto<M>(cvec, p.vec_dv, kapA);
+                eangB = rot_angles_auto<M>(cvec, p.vec_dv, kapB);
             }
         }
         // PROG_H2_CN_H2 follows k_slab, whose one CTA per SM holds the whole register file until it exits: no CTA of this kernel is

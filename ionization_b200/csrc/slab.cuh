@@ -164,7 +164,7 @@ ION_DEVINL void slab_rot_upper(const cplx (&A)[4], cplx (&B)[4], const Trig (&an
 
 // grid = (n_slabs * n_chunks, batch), block = NT (multiple of 32, NT >= G * (Qc + 2)); dynamic smem = 12 * NT cplx
 template <int NTMAX>
-__global__ void __launch_bounds__(NTMAX, 1) k_slab(const SlabParams p)
+__global__ void __launch_bounds__(NTMAX, NTMAX <= 288 ? 2 : 1) k_slab(const SlabParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *xch = reinterpret_cast<cplx *>(smem_raw);  // [2 edges + the upper straddling pair's cos/sin][4 rows][NT]
