@@ -240,6 +240,220 @@ def parity_prefix(sim, problem, batch, fields_all, n_check=32):
             "tolerance": 1e-10, "ok": bool(worst <= 1e-10)}
 
 
+# ---------------------------------------------------------------------------------------------
+# extra.* : the two real multi-GPU partitionings of BASELINE.json (configs[3] and configs[4]), measured in the same process
+# group as the headline (VERDICT r01 "next round" 3).  Bounded: a slice of the pulse around its maximum; rates are per time step.
+# ---------------------------------------------------------------------------------------------
+def _max_over_ranks(ms, distributed):
+    if not distributed:
+        return float(ms)
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def e2e_with_setup(local_rank):
+    """configs[2] end to end through the PUBLIC API, set-up included: SphericalHarmonicSpecification(...)
+    .to_sim() builds the time grid, field series, states, mask and Hamiltonian vectors on the host, run() evolves the whole pulse
+    on the device and fills the datastores at the first and last time (store_data_every = -1, as scans do)."""
+    import ionization_b200 as ion
+    from ionization_b200 import potentials as P
+    from ionization_b200 import states as S
+    from ionization_b200 import units as u
+
+    pw, rb = 200 * u.asec, 250 * u.bohr_radius
+    t0 = time.perf_counter()
+    spec = ion.mesh.SphericalHarmonicSpecification(
+        "bench_c3_vel", r_bound=rb, r_points=2000, l_bound=500, time_initial=-5 * pw, time_final=5 * pw, time_step=1 * u.asec,
+        electric_potential=P.SincPulse(pulse_width=pw, fluence=1 * u.Jcm2, phase=0, window=P.LogisticWindow(window_time=4 * pw, window_width=0.2 * pw)),
+        use_numeric_eigenstates=False, test_states=[S.HydrogenBoundState(n, l) for n in range(1, 4) for l in range(n)],
+        mask=P.RadialCosineMask(inner_radius=0.8 * rb, outer_radius=rb, smoothness=8), operators=ion.mesh.SphericalHarmonicVelocityGaugeOperators(),
+        evolution_method=ion.mesh.SplitInteractionOperator(), store_data_every=-1, device=local_rank,
+    )
+    sim = spec.to_sim()
+    t1 = time.perf_counter()
+    sim.run()
+    norm = float(sim.data.norm[-1])
+    t2 = time.perf_counter()
+    updates = (sim.time_steps - 1) * 2000 * 500
+    return {"value": updates / (t2 - t0), "unit": "updates/s", "setup_s": t1 - t0, "run_s": t2 - t1, "final_norm": norm,
+            "api": "ionization_b200.mesh.SphericalHarmonicSpecification(...).to_sim().run(), wall clock, first call in the process (LU factors + graph capture included)"}
+
+
+def _all_ok(ok, distributed):
+    """collective vote: did every rank get through its (collective-free) set-up?  Keeps the ranks in step when one of them fails."""
+    if not distributed:
+        return bool(ok)
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(int(t[0]))
+
+
+def extra_c4_scan(rank, world, local_rank, stream, n_t=200, n_fluence=64, n_phase=64):
+    """configs[3]: the 4096-member fluence x CEP scan (ionization_scans/scan_mesh.py:40-75) split as 4096 / N members per rank
+    (strong scaling, no data-path collective), per-member norm and ionization fraction gathered inside the timed region
+    (scan_utils.py:638-663 returns each finished sim to the submitter)."""
+    import torch
+
+    from ionization_b200 import _native as nat
+    from ionization_b200 import coefficients as C
+    from ionization_b200 import configs, engine, parallel
+    from ionization_b200 import units as u
+
+    distributed = world > 1
+    p = configs.config4_member("LEN")
+    L, R = int(p["L"]), int(p["R"])
+    total = n_fluence * n_phase
+    b0, b1 = parallel.shard_range(total, rank, world)
+    nb = b1 - b0
+    flu = np.geomspace(0.01, 20, n_fluence) * u.Jcm2
+    ph = np.linspace(0, u.twopi, n_phase, endpoint=False)
+    start = 1000 - n_t // 2
+    times = p["times"][start : start + n_t + 1]
+    cols = [C.field_series("sh_len_so", configs.sinc_pulse(200 * u.asec, flu[m // n_phase], ph[m % n_phase]), times, p["time_step"]) for m in range(b0, b1)]
+    fields = np.ascontiguousarray(np.array(cols).T)
+    taus = np.ascontiguousarray(p["taus"][start : start + n_t])
+    what = nat.OBS_NORM | nat.OBS_INNER_PRODUCTS
+    mask = np.zeros(n_t, dtype=np.uint8)
+    mask[-1] = 1
+    bound = np.asarray(p["state_bound"]).astype(bool)
+    sim, err = None, None
+    try:
+        sim = engine.DeviceSimulation.from_problem(p, batch=nb, device=local_rank)
+        sim.set_stream(stream.cuda_stream)
+        sim.run(taus, fields, mask, what)  # warm-up: LU factors, graph capture
+        sim.write_g_broadcast(p["g0"])
+    except Exception as exc:  # noqa: BLE001
+        err = f"{type(exc).__name__}: {exc}"
+    if not _all_ok(err is None, distributed):
+        if sim is not None:
+            sim.close()
+        return {"error": err or "set-up failed on another rank"}
+    with sim:
+        torch.cuda.synchronize()
+        l0 = sim.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        rec = sim.run(taus, fields, mask, what)[0]  # [nb, 1 + 2 n_states]
+        e1.record(stream)
+        e1.synchronize()
+        ips = rec[:, 1:].reshape(nb, -1, 2)
+        ov = ips[..., 0] ** 2 + ips[..., 1] ** 2
+        mine = {"first_member": b0, "norm": rec[:, 0].copy(), "ionization_fraction": 1.0 - ov[:, bound].sum(axis=1)}
+        gathered = parallel.gather_objects(mine) if distributed else [mine]
+        wall = time.perf_counter() - t0
+        ms = _max_over_ranks(e0.elapsed_time(e1), distributed)
+        launches = sim.launch_count - l0
+    norms = np.concatenate([g["norm"] for g in sorted(gathered, key=lambda g: g["first_member"])])
+    peak, _ = measured_peak_gbs()
+    rate = total * L * R * n_t / (ms * 1e-3)
+    return {
+        "workload": f"configs[3]: {total}-member fluence x CEP scan, SphericalHarmonicMesh 1000x200 LEN split-operator; {n_t} of 2000 time steps around the pulse maximum",
+        "members": total, "members_per_rank": nb, "time_steps": n_t, "ms_per_step": ms / n_t, "updates_per_s": rate, "scaling": "strong",
+        "hbm_roofline_frac_per_gpu": rate / world * BYTES_PER_UPDATE / (peak * 1e9), "gather_wall_s_incl_run": wall, "members_gathered": int(len(norms)),
+        "norm_min": float(norms.min()), "norm_max": float(norms.max()), "gpu_launches_per_rank": int(launches), "collective": "none on the data path; all_gather_object of per-member scalars at the end",
+    }
+
+
+def extra_c5_sharded(rank, world, local_rank, n_t=100):
+    """configs[4]: one SphericalHarmonicMesh simulation r_points=16384, l_bound=4096 (length gauge), l-block sharded over the
+    ranks with the engine's peer-memory halo exchange inside the captured step loop (csrc/halo.cuh).  At N = 1: the
+    unsharded run.  Parity: the gathered shards against the unsharded run on rank 0, same steps."""
+    import torch
+
+    from ionization_b200 import _native as nat
+    from ionization_b200 import configs, engine, parallel
+    from ionization_b200 import units as u
+
+    distributed = world > 1
+    R, L = 16384, 4096
+    p = configs.spherical_harmonic_problem(r_bound=0.1 * R * u.bohr_radius, r_points=R, l_bound=L, gauge="LEN", n_steps=n_t,
+                                           pulse=configs.sinc_pulse(20 * u.asec, 20 * u.Jcm2), time_initial=-n_t / 2 * u.asec, time_final=n_t / 2 * u.asec)
+    rng = np.random.default_rng(5)
+    g0 = (rng.standard_normal((L, R)) + 1j * rng.standard_normal((L, R))) * np.exp(-((p["r"] / p["r"][-1]) ** 2) * 3)[None, :]
+    g0 *= np.exp(-np.arange(L) / (L / 4))[:, None]
+    p["g0"] = g0 / np.sqrt(np.sum(np.abs(g0) ** 2) * float(p["delta_r"]))
+    del g0
+    out = {"workload": f"configs[4]: SphericalHarmonicMesh r_points={R} l_bound={L} LEN split-operator, {n_t} time steps, one simulation", "time_steps": n_t, "scaling": "strong"}
+    peak, _ = measured_peak_gbs()
+
+    def unsharded(env):
+        keep = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            with engine.DeviceSimulation.from_problem(p, device=local_rank) as sim:
+                st = torch.cuda.Stream()
+                sim.set_stream(st.cuda_stream)
+                sim.step(p["taus"], p["fields"])
+                sim.write_g_broadcast(p["g0"])
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                sim.step(p["taus"], p["fields"])
+                e1.record(st)
+                e1.synchronize()
+                return e0.elapsed_time(e1) / n_t, sim.read_g()[0]
+        finally:
+            for k, v in keep.items():
+                os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+
+    if not distributed:
+        ms, _ = unsharded({})
+        out.update({"ms_per_step": ms, "updates_per_s": R * L / (ms * 1e-3), "hbm_roofline_frac_per_gpu": R * L / (ms * 1e-3) * BYTES_PER_UPDATE / (peak * 1e9),
+                    "partitioning": "unsharded (N = 1): r-segmented kernels, folded length-gauge step"})
+        return out
+    import torch.distributed as dist
+
+    shard, err = None, None
+    try:
+        shard = parallel.ShardedSimulation(p, rank, world, device=local_rank)
+    except Exception as exc:  # noqa: BLE001
+        err = f"{type(exc).__name__}: {exc}"
+    if not _all_ok(err is None, True):
+        if shard is not None:
+            shard.close()
+        return {"error": err or "set-up failed on another rank"}
+    shard.attach_peers()
+    shard.step_device(p["taus"], p["fields"])  # warm-up: LU factors, graph capture
+    shard.engine.synchronize()
+    shard.engine.write_g(np.asarray(p["g0"])[shard.l_begin : shard.l_begin + shard.L].reshape(1, shard.L, R))
+    dist.barrier()
+    torch.cuda.synchronize()
+    l0 = shard.engine.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(shard.stream)
+    shard.step_device(p["taus"], p["fields"])
+    e1.record(shard.stream)
+    e1.synchronize()
+    ms = _max_over_ranks(e0.elapsed_time(e1), True) / n_t
+    launches = shard.engine.launch_count - l0
+    n_ex, aborted = shard.engine.halo_status()
+    rec = parallel.all_reduce_observation(shard.partial_observation(nat.OBS_NORM), device=local_rank)
+    blocks = parallel.gather_objects((shard.l_begin, shard.read_g()))
+    shard.close()
+    out.update({"ms_per_step": ms, "updates_per_s": R * L / (ms * 1e-3), "hbm_roofline_frac_per_gpu": R * L / (ms * 1e-3) / world * BYTES_PER_UPDATE / (peak * 1e9),
+                "partitioning": f"{world} contiguous l-blocks of {L // world} channels cut at even channels, one ghost channel per neighbour",
+                "halo_bytes_per_exchange_per_neighbour": R * 16, "exchanges_per_step": len(shard.halo_phases), "exchanges_done": n_ex, "halo_aborted": bool(aborted),
+                "transport": "engine kernel over NVLink peer memory (CUDA IPC), inside the captured step loop; NCCL only for rendezvous and the scalar all-reduce",
+                "norm": float(rec[0]), "gpu_launches_per_rank": int(launches)})
+    if rank == 0:
+        ms_same, g_ref = unsharded({"ION_NO_LEN_FOLD": "1"})
+        ms_best, _ = unsharded({})
+        g = np.concatenate([blk for _, blk in sorted(blocks, key=lambda x: x[0])], axis=0)
+        out.update({"max_rel_err_vs_unsharded": float(np.max(np.abs(g - g_ref)) / np.max(np.abs(g_ref))),
+                    "unsharded_1gpu_ms_per_step_same_kernels": ms_same, "unsharded_1gpu_ms_per_step_best": ms_best,
+                    "efficiency_vs_1gpu_same_kernels": ms_same / (world * ms), "efficiency_vs_1gpu_best": ms_best / (world * ms)})
+    dist.barrier()
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -291,6 +505,7 @@ def main():
     ap.add_argument("--time-steps", type=int, default=None, help="time steps per bench step (default: the workload's full pulse)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed self-check against the oracle")
+    ap.add_argument("--no-extras", action="store_true", help="skip extra.c4_scan / extra.c5_sharded (the two multi-GPU partitionings)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -331,7 +546,7 @@ def main():
     what = nat.OBS_NORM | nat.OBS_INNER_PRODUCTS
 
     # pinned host buffers for the end-to-end path
-    g0_full = np.ascontiguousarray(np.broadcast_to(np.asarray(problem["g0"], dtype=np.complex128).reshape(1, L, R), (batch, L, R)))
+    g0_full = np.array(np.broadcast_to(np.asarray(problem["g0"], dtype=np.complex128).reshape(1, L, R), (batch, L, R)), order="C", copy=True)
     g0_pinned = torch.from_numpy(g0_full.view(np.float64).reshape(batch, L, R, 2)).pin_memory()
     g0_np = g0_pinned.numpy().view(np.complex128).reshape(batch, L, R)
     gout_pinned = torch.empty((batch, L, R, 2), dtype=torch.float64).pin_memory()
@@ -476,6 +691,23 @@ def main():
         except Exception as exc:  # the checker is optional at bench time
             cpu_baseline = {"value": None, "unit": "updates/s", "cores": 0, "kind": "port", "sample": f"unavailable: {exc}"}
 
+    sim.close()
+    with_setup = None
+    if rank == 0 and args.workload == "c3_vel" and not args.no_extras:
+        try:
+            with_setup = e2e_with_setup(local_rank)
+        except Exception as exc:  # noqa: BLE001
+            with_setup = {"error": f"{type(exc).__name__}: {exc}"}
+    extra = None
+    if args.workload == "c3_vel" and not args.no_extras:
+        extra = {}
+        for name, fn in (("c4_scan", lambda: extra_c4_scan(rank, world, local_rank, stream)), ("c5_sharded", lambda: extra_c5_sharded(rank, world, local_rank))):
+            try:
+                extra[name] = fn()
+            except Exception as exc:  # an extra must never take the headline down with it
+                extra[name] = {"error": f"{type(exc).__name__}: {exc}"}
+                if distributed:  # the ranks may be out of step now: no further collectives
+                    break
     if rank == 0:
         line = {
             "metric": "grid-point updates/s (SphericalHarmonicMesh CN+split)", "value": value, "unit": "updates/s", "n_gpus": world, "steps": args.steps,
@@ -485,11 +717,10 @@ def main():
                        "l2": "flushed between timed iterations (256 MB write); psi (16 B/pt) + CN factors (16 B/pt) are L2-resident within an iteration by design"},
             "hbm_roofline_frac_step": value / world * BYTES_PER_UPDATE / (peak * 1e9), "us_per_time_step": 1e3 * ms / args.steps / n_t,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
-            "e2e": {"value": value_e2e, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,
+            "e2e": {"value": value_e2e, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, "with_setup": with_setup},
+            "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall, "extra": extra,
         }
         print(json.dumps(line), flush=True)
-    sim.close()
     if distributed:
         dist.destroy_process_group()
 

@@ -123,6 +123,9 @@ int ion_sim_set_observables(ion_sim_t *sim, double inner_product_multiplier, con
 /* g <-> host, reference layout [batch][L][R]. */
 int ion_sim_write_g(ion_sim_t *sim, const void *g);
 int ion_sim_read_g(ion_sim_t *sim, void *g);
+/* the same initial state for every member of an ensemble (ionization_scans/scan_mesh.py:40-68 gives every member the
+ * same initial_state): g is ONE member, [L][R]; it is copied to the device once and replicated there. */
+int ion_sim_write_g_broadcast(ion_sim_t *sim, const void *g);
 
 /* Advance n_steps time steps (each = QuantumMesh.evolve(): evolution operators then mask).
  *   taus   float64 [n_steps]          tau_n = (t_n - t_{n-1}) / (2 hbar)   (evolution_methods.py:92)

@@ -61,6 +61,7 @@ SIGNATURES = {
     "ion_sim_set_observables": (_i32, [_vp, _f64, _vp, _i64, _vp, _vp, _i64, _vp]),
     "ion_sim_write_g": (_i32, [_vp, _vp]),
     "ion_sim_read_g": (_i32, [_vp, _vp]),
+    "ion_sim_write_g_broadcast": (_i32, [_vp, _vp]),
     "ion_sim_step": (_i32, [_vp, _i64, _vp, _vp]),
     "ion_sim_observation_size": (_i64, [_vp, _u32]),
     "ion_sim_observe": (_i32, [_vp, _u32, _vp]),

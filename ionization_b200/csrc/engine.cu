@@ -133,6 +133,16 @@ struct ion_sim {
     cplx *state_rows = nullptr;
     int *state_first = nullptr, *state_order = nullptr;
     double *partial = nullptr, *ip_out = nullptr, *obs_out = nullptr;
+    double *slab_partial = nullptr, *slab_ip = nullptr;  // per-slab partial sums of the fused observation (slab.cuh)
+    unsigned *obs_counter = nullptr;                     // [batch] CTAs of k_slab_obs_assemble that are done
+    // the record assembly of a fused observation runs on a side branch of the captured graph, so that the next step's kernels
+    // depend on k_slab only: slab_partial / slab_ip are double-buffered (obs_parity), ev_fork orders assemble after its k_slab,
+    // ev_done[k] lets the k_slab that reuses buffer k (two observations later) and the end of a chunk wait for the assembly
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_done[2] = {nullptr, nullptr};
+    bool side_pending[2] = {false, false};
+    int obs_parity = 0;
+    size_t slab_partial_half = 0, slab_ip_half = 0;
     size_t obs_cap = 0;
 
     double vec_dv = 0.0;  // length gauge: increment of the coupling vector per radial row when it is linear to rounding, else 0
@@ -175,6 +185,13 @@ struct ion_sim {
         for (void *p : ptrs)
             if (p) cudaFree(p);
         if (psi2) cudaFree(psi2);
+        if (slab_partial) cudaFree(slab_partial);
+        if (slab_ip) cudaFree(slab_ip);
+        if (obs_counter) cudaFree(obs_counter);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        for (auto e : ev_done)
+            if (e) cudaEventDestroy(e);
+        if (side) cudaStreamDestroy(side);
         if (scal_chunk) cudaFree(scal_chunk);
         if (scal_phase) cudaFree(scal_phase);
         if (th) cudaFree(th);
@@ -255,7 +272,7 @@ void prof_end(ion_sim *s)
 size_t unit_smem_bytes(const ion_sim *s, int prog = -1)
 {
     size_t n = (256 + 4 * (size_t)s->Tc) * sizeof(cplx);
-    const bool cn_pair = (prog == ion::PROG_ROT_CN_ROT || prog == ion::PROG_H2_CN_H2 || prog == ion::PROG_LEN_STEP || prog < 0);
+    const bool cn_pair = (prog == ion::PROG_ROT_CN_ROT || prog == ion::PROG_H2_CN_H2 || prog == ion::PROG_LEN_STEP || prog == ion::PROG_LEN_STEP_OBS || prog < 0);
     if (cn_pair && s->M == 4 && s->S == 1 && s->tmax <= 512) n += 8 * (size_t)s->Tc * sizeof(cplx) + 9 * (size_t)(s->Tc / 2) * sizeof(double);
     return n;
 }
@@ -296,7 +313,7 @@ template <int PROG>
 int set_unit_smem_attr()
 {
     CUDA_TRY(cudaFuncSetAttribute(ion::k_unit<4, PROG, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    if (PROG == ion::PROG_ROT_CN_ROT || PROG == ion::PROG_H2_CN_H2 || PROG == ion::PROG_LEN_STEP) {
+    if (PROG == ion::PROG_ROT_CN_ROT || PROG == ion::PROG_H2_CN_H2 || PROG == ion::PROG_LEN_STEP || PROG == ion::PROG_LEN_STEP_OBS) {
         CUDA_TRY(cudaFuncSetAttribute(ion::k_unit<4, PROG, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(ion::k_unit<4, PROG, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
     }
@@ -312,7 +329,7 @@ int prepare_kernels(ion_sim *s)
         (rc = set_unit_smem_attr<ion::PROG_H2>()) || (rc = set_unit_smem_attr<ion::PROG_H2_CN_H2>()) ||
         (rc = set_unit_smem_attr<ion::PROG_CN>()) || (rc = set_unit_smem_attr<ion::PROG_LINE_SO_LEN>()) ||
         (rc = set_unit_smem_attr<ion::PROG_LINE_SO_VEL>()) || (rc = set_unit_smem_attr<ion::PROG_LINE_CN>()) ||
-        (rc = set_unit_smem_attr<ion::PROG_LEN_STEP>()))
+        (rc = set_unit_smem_attr<ion::PROG_LEN_STEP>()) || (rc = set_unit_smem_attr<ion::PROG_LEN_STEP_OBS>()))
         return rc;
     return ION_OK;
 }
@@ -342,6 +359,13 @@ ion::UnitParams base_params(ion_sim *s)
     p.H = s->H;
     p.l_begin = s->l_begin;
     p.short_scan = s->short_scan;
+    p.obs_rvec = s->rvec;
+    p.obs_state_rows = s->state_rows;
+    p.obs_state_first = s->state_first;
+    p.obs_state_order = s->state_order;
+    p.obs_partial = s->partial;
+    p.obs_ip = s->ip_out;
+    p.obs_ipm = s->ipm;
     p.vec_dv = s->vec_dv;
     p.unit0 = 0;
     p.unit_stride = 1;
@@ -349,12 +373,17 @@ ion::UnitParams base_params(ion_sim *s)
 }
 
 int launch_len_ens(ion_sim *s, const ion::UnitParams &p);
+int launch_observe_finish(ion_sim *s, uint32_t what, double *dev_out);
 
-int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, const double *sb)
+int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, const double *sb, uint32_t obs_what = 0)
 {
     ion::UnitParams p = base_params(s);
     p.parity = parity;
     p.flags = flags;
+    p.obs_what = obs_what;
+    p.obs_n_radii = (obs_what & ION_OBS_NORM_WITHIN) ? s->n_radii : 0;
+    p.obs_n_states = (obs_what & ION_OBS_INNER_PRODUCTS) ? s->n_states : 0;
+    for (int q = 0; q < p.obs_n_radii; ++q) p.obs_radii[q] = s->radii[q];
     if ((flags & ion::F_MASK) && !s->mask) p.flags &= ~ion::F_MASK;
     p.scal_a = sa;
     p.scal_b = sb;
@@ -371,7 +400,7 @@ int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, c
     if (prog == ion::PROG_ROT) p.H = 0;  // point-wise in r: interior threads only
     // r-segments: a kernel that reads halo rows (every program but the point-wise rotation) must not run in place
     // the ADI solve goes back to the buffer the l-pass read from, so that a step ends where it began
-    const bool seg_oop = (s->S > 1 && prog != ion::PROG_ROT && prog != ion::PROG_LEN_STEP) || (prog == ion::PROG_CN && (flags & ion::F_SOLVE_ONLY));
+    const bool seg_oop = (s->S > 1 && prog != ion::PROG_ROT && prog != ion::PROG_LEN_STEP && prog != ion::PROG_LEN_STEP_OBS) || (prog == ion::PROG_CN && (flags & ion::F_SOLVE_ONLY));
     if (seg_oop) {
         if (!s->psi2) return fail(ION_ESTATE, "internal: second wavefunction buffer missing for a segmented kernel");
         p.psi_out = s->psi2;
@@ -427,6 +456,13 @@ int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, c
                 prof_begin(s, kind);
                 rc = launch_unit_prog<ion::PROG_LEN_STEP>(s, p, grid);
             }
+            std::swap(s->psi, s->psi2);
+            break;
+        case ion::PROG_LEN_STEP_OBS:  // never the persistent ensemble kernel: the observed step runs one CTA per (unit, member)
+            kind = KK_LEN_STEP;
+            p.psi_out = s->psi2;
+            prof_begin(s, kind);
+            rc = launch_unit_prog<ion::PROG_LEN_STEP_OBS>(s, p, grid);
             std::swap(s->psi, s->psi2);
             break;
         default: return fail(ION_EINVAL, "unknown unit program");
@@ -633,11 +669,7 @@ int slab_prepare(ion_sim *s)
         const int v = std::atoi(env);
         if (v == 4 || v == 8 || v == 16 || v == 32) G = v;
     }
-    int nt_cap = 512;  // threads per CTA: 512 -> one CTA per SM (128 registers); <= 288 -> two co-resident CTAs per SM
-    if (const char *env = std::getenv("ION_SLAB_NT")) {
-        const int v = std::atoi(env);
-        if (v >= 64 && v <= 512) nt_cap = v;
-    }
+    const int nt_cap = 512;  // one 512-thread CTA per SM at 128 registers (two co-resident 288-thread CTAs at 96 registers spill: measured 32.3 vs 27.6 us per VEL step)
     const int nQ = (s->L + 3) / 4;
     int chunks = 1, Qc = nQ, loaded = nQ;
     for (;; ++chunks) {
@@ -655,13 +687,14 @@ int slab_prepare(ion_sim *s)
     s->slab_slabs = s->R / W + 1;
     s->slab_threads = (G * loaded + 31) / 32 * 32;
     if (int rc = ensure_second_buffer(s)) return rc;
-    CUDA_TRY(cudaFuncSetAttribute(ion::k_slab<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 512 * (int)sizeof(cplx)));
-    CUDA_TRY(cudaFuncSetAttribute(ion::k_slab<288>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 288 * (int)sizeof(cplx)));
+    CUDA_TRY(cudaFuncSetAttribute(ion::k_slab<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 512 * (int)sizeof(cplx)));
+    CUDA_TRY(cudaFuncSetAttribute(ion::k_slab<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 512 * (int)sizeof(cplx)));
     s->slab_state = 1;
     return ION_OK;
 }
 
-int launch_slab(ion_sim *s, const double *sa, const double *sb)
+// obs_what != 0: the state after this step's mask is observed INSIDE the kernel (slab.cuh: SlabObs) and the record goes to obs_dst
+int launch_slab(ion_sim *s, const double *sa, const double *sb, uint32_t obs_what, double *obs_dst)
 {
     ion::SlabParams p;
     std::memset(&p, 0, sizeof(p));
@@ -692,12 +725,47 @@ int launch_slab(ion_sim *s, const double *sa, const double *sb)
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = s->use_pdl ? 1 : 0;
+    ion::SlabObs o;
+    std::memset(&o, 0, sizeof(o));
     prof_begin(s, KK_SLAB);
-    if (s->slab_threads <= 288) CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_slab<288>, p));
-    else CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_slab<512>, p));
+    if (!obs_what) {
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_slab<false>, p, o));
+    } else {
+        if (!s->slab_partial || !s->slab_ip) return fail(ION_ESTATE, "internal: fused-observation buffers missing");
+        o.rvec = s->rvec;
+        o.state_rows = s->state_rows;
+        o.state_first = s->state_first;
+        o.state_order = s->state_order;
+        const int k = s->obs_parity;
+        o.partial = s->slab_partial + (size_t)k * s->slab_partial_half;
+        o.ip = s->slab_ip + (size_t)k * s->slab_ip_half;
+        if (s->side_pending[k]) {  // the assembly that last read this half (two observations ago) must be done
+            CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_done[k], 0));
+            s->side_pending[k] = false;
+        }
+        o.n_radii = (obs_what & ION_OBS_NORM_WITHIN) ? s->n_radii : 0;
+        o.n_states = (obs_what & ION_OBS_INNER_PRODUCTS) ? s->n_states : 0;
+        for (int q = 0; q < o.n_radii; ++q) o.radii[q] = s->radii[q];
+        o.what = obs_what;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_slab<true>, p, o));
+    }
     prof_end(s);
     s->launch_count++;
     std::swap(s->psi, s->psi2);
+    if (obs_what) {
+        // side branch: assemble the record while the main stream goes on with the next step
+        const int k = s->obs_parity;
+        s->obs_parity ^= 1;
+        CUDA_TRY(cudaEventRecord(s->ev_fork, s->stream));
+        CUDA_TRY(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
+        ion::k_slab_obs_assemble<<<dim3(s->L + (2 * o.n_states + 63) / 64, s->batch), 128, 0, s->side>>>(
+            o.partial, o.ip, s->partial, s->ip_out, s->obs_counter, obs_dst, s->slab_slabs, s->L, o.n_states, o.n_radii, (unsigned)obs_what, s->ipm,
+            (long long)ion_sim_observation_size(s, obs_what));
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(s->ev_done[k], s->side));
+        s->side_pending[k] = true;
+        s->launch_count++;
+    }
     return ION_OK;
 }
 
@@ -785,7 +853,15 @@ int fuse_level(const ion_sim *s) { return s->slab_state == 1 ? 2 : 1; }
 // one step; `pre`: how much of this step's head was already done by the previous step's tail (0: nothing, 1: the leading
 // even rotation, 2: velocity gauge with the inter-solve kernel -- everything up to the odd-pair Crank-Nicolson kernel);
 // `fuse_next`: fold the head of the next step into this step's tail (to fuse_level()).
-int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, int pre, bool fuse_next)
+// A fused observation (north_star 4): `what` != 0 asks the kernels of this step to reduce an observed state on the fly and
+// to leave the record at `dst`.  cur: the state after THIS step's mask (velocity gauge: inside k_slab); prev: the state after
+// the PREVIOUS step's mask, whose trailing even rotation and mask were deferred into this step's kernel (length gauge).
+struct ObsReq {
+    uint32_t what = 0;
+    double *dst = nullptr;
+};
+
+int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, int pre, bool fuse_next, ObsReq prev = ObsReq(), ObsReq cur = ObsReq())
 {
     using namespace ion;
     int rc = ION_OK;
@@ -793,7 +869,13 @@ int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, int pre, b
         case ION_SH_LEN_SO:
             if (fast_l_path(s) && s->len_fold_state == 1) {
                 // the previous step's deferred tail (its scalar is the row before sa), the mask and this step's head ride along
-                if ((rc = launch_unit(s, PROG_LEN_STEP, 1, pre ? F_MASK : 0, sa, pre ? sa - s->batch : nullptr))) return rc;
+                if (prev.what && pre) {
+                    if ((rc = launch_unit(s, PROG_LEN_STEP_OBS, 1, F_MASK, sa, sa - s->batch, prev.what))) return rc;
+                    prof_begin(s, KK_OBSERVE);
+                    rc = launch_observe_finish(s, prev.what, prev.dst);
+                    prof_end(s);
+                    if (rc) return rc;
+                } else if ((rc = launch_unit(s, PROG_LEN_STEP, 1, pre ? F_MASK : 0, sa, pre ? sa - s->batch : nullptr))) return rc;
                 return fuse_next ? ION_OK : launch_unit(s, PROG_ROT, 0, F_MASK, sa, nullptr);
             }
             if (fast_l_path(s)) {
@@ -820,7 +902,7 @@ int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, int pre, b
             if (pre < 2 && (rc = launch_unit(s, PROG_H2, 0, 0, sa, nullptr))) return rc;   // ee, eo
             if ((rc = launch_exchange(s))) return rc;
             if ((rc = launch_unit(s, PROG_H2_CN_H2, 1, 0, sa, nullptr))) return rc;        // oe, oo, CN, oo, oe
-            if (fast && fuse_next && s->slab_state == 1) return launch_slab(s, sa, sb_next);  // eo ee h1_o h1_e mask | h1_e h1_o ee eo
+            if (fast && fuse_next && s->slab_state == 1) return launch_slab(s, sa, sb_next, cur.what, cur.dst);  // eo ee h1_o h1_e mask | h1_e h1_o ee eo
             if ((rc = launch_unit(s, PROG_H2, 0, F_H2_REVERSE, sa, nullptr))) return rc;   // eo, ee
             if (fast) {
                 if ((rc = launch_exchange(s))) return rc;
@@ -926,12 +1008,30 @@ int launch_observe(ion_sim *s, uint32_t what, double *dev_out)
     prof_begin(s, KK_OBSERVE);
     ion::k_observe<<<dim3(s->L_own, s->batch), 256, 0, s->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
-    long long rec = ion_sim_observation_size(s, what);
-    ion::k_observe_finish<<<(s->batch + 63) / 64, 64, 0, s->stream>>>(s->partial, s->ip_out, dev_out, s->batch, s->L_own, p.n_states,
-                                                                     p.n_radii, what, s->ipm, rec);
+    s->launch_count++;
+    int rc = launch_observe_finish(s, what, dev_out);
     prof_end(s);
-    s->launch_count += 2;
-    CUDA_TRY(cudaGetLastError());
+    return rc;
+}
+
+// record assembly from the per-channel partial sums and the inner products (left by k_observe or by a kernel with a fused observation)
+int launch_observe_finish(ion_sim *s, uint32_t what, double *dev_out)
+{
+    const int n_states = (what & ION_OBS_INNER_PRODUCTS) ? s->n_states : 0, n_radii = (what & ION_OBS_NORM_WITHIN) ? s->n_radii : 0;
+    const long long rec = ion_sim_observation_size(s, what);
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(s->batch);
+    cfg.blockDim = dim3(256);
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = s->use_pdl ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_observe_finish, (const double *)s->partial, (const double *)s->ip_out, dev_out, s->batch, s->L_own, n_states, n_radii,
+                                (unsigned)what, s->ipm, rec));
+    s->launch_count++;
     return ION_OK;
 }
 
@@ -962,25 +1062,65 @@ const int64_t GRAPH_CHUNK = [] {
     return (int64_t)64;
 }();
 
+// the main stream waits for the record assemblies still running on the side branch (they use partial / ip_out, which
+// k_observe is about to overwrite; and a captured chunk must join everything it forked)
+int join_side(ion_sim *s)
+{
+    for (int k = 0; k < 2; ++k)
+        if (s->side_pending[k]) {
+            CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_done[k], 0));
+            s->side_pending[k] = false;
+        }
+    return ION_OK;
+}
+
+// Can the observation of a step ride on the fused schedule?  Point-wise observables only (<z> and <H0> couple neighbouring
+// channels / rows across CTA edges); velocity gauge with the inter-solve kernel, or the folded length-gauge step; one CTA per channel.
+bool obs_fusable(const ion_sim *s, uint32_t what)
+{
+    const char *e = std::getenv("ION_NO_FUSED_OBS");  // A/B switch: every observed step on the single-sweep schedule + k_observe
+    if ((e && e[0] == '1') || !what || s->S != 1 || s->M != 4) return false;
+    if (what & ~(ION_OBS_NORM | ION_OBS_INNER_PRODUCTS | ION_OBS_NORM_BY_L | ION_OBS_R | ION_OBS_NORM_WITHIN)) return false;
+    if (s->program == ION_SH_VEL_SO) return s->slab_state == 1 && s->slab_partial && s->slab_ip;
+    if (s->program == ION_SH_LEN_SO) return s->len_fold_state == 1;
+    return false;
+}
+
 // enqueue steps [n0, n0+len) reading scalars from `scal` (row n - n0 of it) and writing observations to `obs`
 int enqueue_steps(ion_sim *s, int64_t len, const double *scal, const uint8_t *pattern, bool pre_done_first, bool fuse_last,
                   uint32_t what, double *obs, size_t rec, bool *pre_done_out)
 {
     const bool can_fuse = program_fuses(s);
+    const bool fuse_obs = can_fuse && obs_fusable(s, what);
+    const bool vel = s->program == ION_SH_VEL_SO;
     bool pre_done = pre_done_first;
     int64_t k_obs = 0;
+    ObsReq pending;  // length gauge: the observation of the previous step, to be made by this step's kernel
     for (int64_t n = 0; n < len; ++n) {
         const bool ob = pattern && pattern[n];
-        const bool fuse_next = can_fuse && !ob && (n + 1 < len ? true : fuse_last);
+        const bool last = n + 1 == len;
+        // an observed step keeps the fused schedule when the reductions can ride along; the last step of a chunk hands a
+        // finished state to whatever follows (the next chunk's graph, the caller), so its observation is a separate pass
+        const bool fuse_next = can_fuse && (!ob || (fuse_obs && !last)) && (last ? fuse_last : true);
         const double *sa = scal + (size_t)n * s->batch;
-        if (int rc = enqueue_step(s, sa, sa + s->batch, pre_done ? fuse_level(s) : 0, fuse_next)) return rc;
+        ObsReq cur;
+        if (ob && fuse_next) {
+            cur.what = what;
+            cur.dst = obs + (size_t)k_obs * rec;
+        }
+        if (int rc = enqueue_step(s, sa, sa + s->batch, pre_done ? fuse_level(s) : 0, fuse_next, pending, vel ? cur : ObsReq())) return rc;
+        pending = vel ? ObsReq() : cur;
         pre_done = fuse_next;
         if (ob) {
-            if (int rc = launch_observe(s, what, obs + (size_t)k_obs * rec)) return rc;
+            if (!fuse_next) {
+                if (int rc = join_side(s)) return rc;
+                if (int rc = launch_observe(s, what, obs + (size_t)k_obs * rec)) return rc;
+            }
             ++k_obs;
         }
     }
     if (pre_done_out) *pre_done_out = pre_done;
+    if (int rc = join_side(s)) return rc;
     return restore_home(s);  // a captured chunk must end where it started
 }
 
@@ -1015,6 +1155,23 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
     if (int rc = len_fold_prepare(s)) return rc;
     if (s->S > 1 || s->program == ION_SH_LEN_ADI)
         if (int rc = ensure_second_buffer(s)) return rc;  // segmented kernels run out of place
+    if (n_obs && s->slab_state == 1) {  // per-slab partial sums of the fused observation (slab.cuh)
+        s->slab_partial_half = (size_t)s->batch * s->slab_slabs * s->L * (4 + ION_MAX_RADII);
+        s->slab_ip_half = (size_t)s->batch * s->slab_slabs * std::max(s->n_states, 1) * 2;
+        if (!s->slab_partial)
+            if (int rc = dev_alloc(&s->slab_partial, 2 * s->slab_partial_half)) return rc;
+        if (!s->slab_ip)
+            if (int rc = dev_alloc(&s->slab_ip, 2 * s->slab_ip_half)) return rc;
+        if (!s->side) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+            for (auto &e : s->ev_done) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        if (!s->obs_counter) {
+            if (int rc = dev_alloc(&s->obs_counter, (size_t)s->batch)) return rc;
+            CUDA_TRY(cudaMemsetAsync(s->obs_counter, 0, (size_t)s->batch * sizeof(unsigned), s->stream));
+        }
+    }
     if (!(s->use_graphs && uniform_tau && !s->profiling && s->stream != 0 && n_steps >= 4)) {
         bool pre_done = false;
         int64_t k_obs = 0;
@@ -1079,13 +1236,8 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
                 if (e != cudaSuccess) return fail(ION_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
                 it = s->graphs.emplace(key, entry).first;
             } else {
-                // same bookkeeping as the capture run
-                bool pd = pre_done;
-                for (int64_t n = 0; n < len; ++n) {
-                    const bool ob = pattern && pattern[n];
-                    pd = can_fuse && !ob && (n + 1 < len ? true : fuse_last);
-                }
-                pre_done_after = pd;
+                // same bookkeeping as the capture run: only the last step of the chunk decides
+                pre_done_after = can_fuse && fuse_last;
             }
             CUDA_TRY(cudaMemcpyAsync(s->scal_chunk, s->scal + (size_t)n0 * s->batch, (size_t)(len + 2) * s->batch * sizeof(double),
                                      cudaMemcpyDeviceToDevice, s->stream));
@@ -1388,6 +1540,10 @@ int ion_sim_set_observables(ion_sim_t *s, double ipm, const double *r_j, int64_t
         cudaFree(s->ip_out);
         s->ip_out = nullptr;
     }
+    if (s->slab_ip) {
+        cudaFree(s->slab_ip);
+        s->slab_ip = nullptr;
+    }
     std::vector<int> first((size_t)s->L_own + 1, 0), order;
     for (int l = 0; l < s->L_own; ++l) {
         first[l] = (int)order.size();
@@ -1412,7 +1568,7 @@ int ion_sim_set_observables(ion_sim_t *s, double ipm, const double *r_j, int64_t
         cudaError_t e = cudaMemcpy(stage, state_rows, (size_t)n_states * s->R * sizeof(cplx), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) {
             dim3 grid((s->Rp + 127) / 128, (unsigned)std::min<int64_t>(n_states, 4096));
-            ion::k_to_internal_c<<<grid, 128, 0, s->stream>>>(stage, s->state_rows, s->R, s->M, s->T, n_states);
+            ion::k_to_internal_c<<<grid, 128, 0, s->stream>>>(stage, s->state_rows, s->R, s->M, s->T, n_states, n_states);
             e = cudaStreamSynchronize(s->stream);
         }
         cudaFree(stage);
@@ -1430,7 +1586,22 @@ int ion_sim_write_g(ion_sim_t *s, const void *g)
         if (int rc = dev_alloc(&s->io_stage, n * s->R)) return rc;
     CUDA_TRY(cudaMemcpyAsync(s->io_stage, g, n * s->R * sizeof(cplx), cudaMemcpyHostToDevice, s->stream));
     dim3 grid((s->Rp + 127) / 128, (unsigned)std::min<size_t>(n, 8192));
-    ion::k_to_internal_c<<<grid, 128, 0, s->stream>>>(s->io_stage, s->psi + (size_t)s->g_lo * s->Rp, s->R, s->M, s->T, (long long)n);
+    ion::k_to_internal_c<<<grid, 128, 0, s->stream>>>(s->io_stage, s->psi + (size_t)s->g_lo * s->Rp, s->R, s->M, s->T, (long long)n, (long long)n);
+    s->launch_count++;
+    CUDA_TRY(cudaGetLastError());
+    return ION_OK;
+}
+
+int ion_sim_write_g_broadcast(ion_sim_t *s, const void *g)
+{
+    if (!s || !g) return fail(ION_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const size_t n = (size_t)s->batch * s->L_own, n1 = (size_t)s->L_own;
+    if (!s->io_stage)
+        if (int rc = dev_alloc(&s->io_stage, n * s->R)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s->io_stage, g, n1 * s->R * sizeof(cplx), cudaMemcpyHostToDevice, s->stream));
+    dim3 grid((s->Rp + 127) / 128, (unsigned)std::min<size_t>(n, 8192));
+    ion::k_to_internal_c<<<grid, 128, 0, s->stream>>>(s->io_stage, s->psi + (size_t)s->g_lo * s->Rp, s->R, s->M, s->T, (long long)n, (long long)n1);
     s->launch_count++;
     CUDA_TRY(cudaGetLastError());
     return ION_OK;

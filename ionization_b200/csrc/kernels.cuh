@@ -52,6 +52,17 @@ struct UnitParams {
     int parity;              // parity (in GLOBAL l) of the lower channel of a pair
     int flags;
     int short_scan;          // reach of the cross-warp inflow of the CN scans in warps (0: full scan; see common.cuh)
+    // fused observation (PROG_LEN_STEP_OBS): the state after the previous step's mask is reduced inside this step's kernel
+    const double *obs_rvec;       // [M][T] permuted r_j
+    const cplx *obs_state_rows;   // [n_states][M][T]
+    const int *obs_state_first;   // [L + 1]
+    const int *obs_state_order;   // [n_states]
+    double *obs_partial;          // [batch][L][4 + n_radii]   (k_observe's layout)
+    double *obs_ip;               // [batch][n_states][2]
+    double obs_radii[8];
+    double obs_ipm;
+    int obs_n_radii, obs_n_states;
+    unsigned obs_what;
     double vec_dv;           // != 0: vec is linear in the row index with this increment per row (length gauge on the uniform radial grid)
     int unit0, unit_stride;  // unit of CTA x = unit0 + x * unit_stride (0, 1: all units; the ensemble kernel leaves the single channels to k_unit)
 };
@@ -497,6 +508,8 @@ enum : int {
     PROG_LINE_CN = 7,    // CN with H = H0 + diag(s w_z): pivots rebuilt every step     -- LineMesh CN (ADI) length gauge
     PROG_LEN_STEP = 8,   // even rotation(s_a + s_b) [+ mask] of the unit's channels with their READ-ONLY even-pair partners,
                          // then rotation(s_a), CN, rotation(s_a) on the odd pair; out of place -- one pass per LEN step
+    PROG_LEN_STEP_OBS = 9,  // the same with the observation of the PREVIOUS step fused in: even rotation(s_b), mask, reductions over
+                            // the unit's own channels, even rotation(s_a), ... (north_star 4; see obs_channel)
 };
 
 // One member of an l-pair rotation [[c, -i s], [-i s, c]] (the matrix is symmetric: both members use the same formula)
@@ -516,6 +529,74 @@ ION_DEVINL bool even_partner(const UnitParams &p, int c, int &pc, int &ci)
     pc = (gl & 1) ? c - 1 : c + 1;
     ci = (gl & 1) ? gl - 1 : gl;
     return pc >= 0 && pc < p.L;
+}
+
+// both members of an even pair [[c, -i s], [-i s, c]] from their old values (the partner is read-only in memory, but the
+// fused observation needs ITS post-rotation value too: the next half-rotation of X acts on the rotated pair)
+template <int M>
+ION_DEVINL void rotate_both(cplx (&X)[M], cplx (&Q)[M], const RotAngles<M> &ang)
+{
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        const cplx x = X[k], q = Q[k];
+        X[k] = c_make(fma(ang.c[k], x.x, ang.s[k] * q.y), fma(ang.c[k], x.y, -ang.s[k] * q.x));
+        Q[k] = c_make(fma(ang.c[k], q.x, ang.s[k] * x.y), fma(ang.c[k], q.y, -ang.s[k] * x.x));
+    }
+}
+
+// Fused observation of ONE channel held by the CTA (rows k*T + t of thread t in X): norm, <r>, norm within radii ->
+// obs_partial[b][l] (k_observe's layout; the <z> and <H0> slots are zero: those observables take the unfused path), inner
+// products with the channel's test states -> obs_ip.  CTA-wide reductions in a fixed order (deterministic).  sm: >= 32 * 10 doubles.
+#ifndef ION_MAX_RADII
+#define ION_MAX_RADII 8
+#endif
+template <int M>
+ION_DEVINL void obs_channel(const UnitParams &p, const cplx (&X)[M], int l, int b, int t, bool ok, int tl, int Tc, double *sm)
+{
+    const int T = p.T;
+    double n2[M], rr[M], acc[2] = {0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        n2[k] = ok ? c_abs2(X[k]) : 0.0;  // padding rows are zero
+        rr[k] = (ok && p.obs_rvec) ? p.obs_rvec[k * T + t] : 0.0;
+        acc[0] += n2[k];
+        acc[1] += rr[k] * n2[k];
+    }
+    block_sum<2>(acc, sm, tl, Tc);
+    double *out = p.obs_partial + ((size_t)b * p.L + l) * (4 + p.obs_n_radii);
+    if (tl == 0) {
+        out[0] = acc[0];
+        out[1] = acc[1];
+        out[2] = 0.0;
+        out[3] = 0.0;
+    }
+    for (int q = 0; q < p.obs_n_radii; ++q) {  // norm within radius q (mesh/data.py:419-422)
+        double w[1] = {0.0};
+#pragma unroll
+        for (int k = 0; k < M; ++k) w[0] += (rr[k] <= p.obs_radii[q]) ? n2[k] : 0.0;
+        block_sum<1>(w, sm, tl, Tc);
+        if (tl == 0) out[4 + q] = w[0];
+    }
+    if ((p.obs_what & 2u) && p.obs_n_states > 0) {
+        for (int si = p.obs_state_first[l]; si < p.obs_state_first[l + 1]; ++si) {  // uniform over the CTA
+            const int st = p.obs_state_order[si];
+            const cplx *row = p.obs_state_rows + (size_t)st * M * T;
+            double ip[2] = {0.0, 0.0};
+#pragma unroll
+            for (int k = 0; k < M; ++k) {
+                if (ok) {
+                    const cplx a = row[k * T + t], x = X[k];
+                    ip[0] += a.x * x.x + a.y * x.y;
+                    ip[1] += a.x * x.y - a.y * x.x;
+                }
+            }
+            block_sum<2>(ip, sm, tl, Tc);
+            if (tl == 0) {
+                p.obs_ip[((size_t)b * p.obs_n_states + st) * 2 + 0] = ip[0] * p.obs_ipm;
+                p.obs_ip[((size_t)b * p.obs_n_states + st) * 2 + 1] = ip[1] * p.obs_ipm;
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -696,7 +777,8 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
 
     // ---- programs containing Crank-Nicolson ----
     // pairs: both channels are solved together in layout 2 (see above); single channels and r-segments keep layout 1
-    constexpr bool L2CN = (M == 4) && !SEG && (TMAX <= 512) && (PROG == PROG_ROT_CN_ROT || PROG == PROG_H2_CN_H2 || PROG == PROG_LEN_STEP);
+    constexpr bool LENSTEP = (PROG == PROG_LEN_STEP || PROG == PROG_LEN_STEP_OBS), OBS = (PROG == PROG_LEN_STEP_OBS);
+    constexpr bool L2CN = (M == 4) && !SEG && (TMAX <= 512) && (PROG == PROG_ROT_CN_ROT || PROG == PROG_H2_CN_H2 || LENSTEP);
 #ifdef ION_EXP_CLOCKS  // timing-only instrumentation: phase time stamps of two CTAs (first and second wave)
     long long ck[8];
 #define ION_CK(i) ck[i] = clock64()
@@ -728,12 +810,13 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         // LU factor of the row before the chunk (row 8pp - 1: the previous lane pair's last row, possibly another warp's)
         const cplx wprev = pp > 0 ? ld_c(p.w + (size_t)(l0 + (odd ? 1 : 0)) * chan + 3 * (size_t)T + 2 * pp - 1) : c_zero();
         double cvec[M], czp = 0.0, kap0, kapA = 0.0, kapB = 0.0;
-        if (PROG == PROG_ROT_CN_ROT || PROG == PROG_LEN_STEP) {
+        if (PROG == PROG_ROT_CN_ROT || LENSTEP) {
             load_vec<M>(cvec, p.vec, T, t, true);
             kap0 = sa * p.cl[p.l_begin + l0];
-            if (PROG == PROG_LEN_STEP) {  // a pair always has both even-pair partners: l0 - 1 and l0 + 2
-                kapA = (sa + sb) * p.cl[p.l_begin + l0 - 1];
-                kapB = (sa + sb) * p.cl[p.l_begin + l0 + 1];
+            if (LENSTEP) {  // a pair always has both even-pair partners: l0 - 1 and l0 + 2
+                // OBS: the previous step's half (s_b) first, on its own -- the observed state sits between the two halves
+                kapA = (OBS ? sb : sa + sb) * p.cl[p.l_begin + l0 - 1];
+                kapB = (OBS ? sb : sa + sb) * p.cl[p.l_begin + l0 + 1];
             }
         } else {
             load_vec<M>(cvec, p.zvec, T, t, true);
@@ -758,9 +841,9 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         Q8 = c_mul(aQ0, aQ1);
         RotAngles<M> rang, eangA, eangB;
         RPairAngles<M> pang;
-        if (PROG == PROG_ROT_CN_ROT || PROG == PROG_LEN_STEP) {
+        if (PROG == PROG_ROT_CN_ROT || LENSTEP) {
             rang = rot_angles_auto<M>(cvec, p.vec_dv, kap0);
-            if (PROG == PROG_LEN_STEP) {
+            if (LENSTEP) {
                 eangA = rot_angles_auto<M>(cvec, p.vec_dv, kapA);
                 eangB = rot_angles_auto<M>(cvec, p.vec_dv, kapB);
             }
@@ -779,7 +862,28 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
 #ifndef ION_H2_TRIG_FIRST
         if (PROG == PROG_H2_CN_H2) pang = rpair_angles<M>(cvec, czp, kap0);
 #endif
-        if (PROG == PROG_LEN_STEP) {
+        if constexpr (OBS) {
+            // psi_n = mask E_e(s_b) (...) on the even pairs (l0 - 1, l0) and (l0 + 1, l0 + 2): both members, because this step's
+            // own half-rotation E_e(s_a) then acts on the rotated, masked pair.  The unit's own channels l0, l0 + 1 are observed.
+            double mk[M];
+#pragma unroll
+            for (int k = 0; k < M; ++k) mk[k] = 1.0;
+            if (p.flags & F_MASK) load_vec<M>(mk, p.mask, T, t, true);
+            double *osm = reinterpret_cast<double *>(xs);
+            cplx Q[M];
+            load_rows<M>(Q, base - chan, T, t, true);
+            rotate_both<M>(A, Q, eangA);
+#pragma unroll
+            for (int k = 0; k < M; ++k) A[k] = c_scale(A[k], mk[k]), Q[k] = c_scale(Q[k], mk[k]);
+            obs_channel<M>(p, A, l0, b, t, true, tl, Tc, osm);
+            rotate_member<M>(A, Q, rot_angles_auto<M>(cvec, p.vec_dv, sa * p.cl[p.l_begin + l0 - 1]));
+            load_rows<M>(Q, base + 2 * chan, T, t, true);
+            rotate_both<M>(B, Q, eangB);
+#pragma unroll
+            for (int k = 0; k < M; ++k) B[k] = c_scale(B[k], mk[k]), Q[k] = c_scale(Q[k], mk[k]);
+            obs_channel<M>(p, B, l0 + 1, b, t, true, tl, Tc, osm);
+            rotate_member<M>(B, Q, rot_angles_auto<M>(cvec, p.vec_dv, sa * p.cl[p.l_begin + l0 + 1]));
+        } else if (LENSTEP) {
             cplx Q[M];
             load_rows<M>(Q, base - chan, T, t, true);
             rotate_member<M>(A, Q, eangA);
@@ -795,7 +899,7 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
                 }
             }
         }
-        if (PROG == PROG_ROT_CN_ROT || PROG == PROG_LEN_STEP) rotate_pair<M, false>(A, B, rang);
+        if (PROG == PROG_ROT_CN_ROT || LENSTEP) rotate_pair<M, false>(A, B, rang);
         else h2_pair<M>(A, B, pang, false, tl, Tc, xs);  // (oe, oo)
         ION_CK(3);
         cp_async_wait_all();
@@ -808,7 +912,7 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
             pair_transpose_out(Z, A, B, odd);
         }
         ION_CK(5);
-        if (PROG == PROG_ROT_CN_ROT || PROG == PROG_LEN_STEP) rotate_pair<M, false>(A, B, rang);
+        if (PROG == PROG_ROT_CN_ROT || LENSTEP) rotate_pair<M, false>(A, B, rang);
         else h2_pair<M>(A, B, pang, true, tl, Tc, xs);  // (oo, oe)
         ION_CK(6);
         store_rows<M>(A, obase, T, t, true);
@@ -835,7 +939,7 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
     // trigonometry of the programs that rotate before the solve: also independent of psi
     RotAngles<M> rang;
     RPairAngles<M> pang;
-    if ((PROG == PROG_ROT_CN_ROT || PROG == PROG_LEN_STEP) && pair) {
+    if ((PROG == PROG_ROT_CN_ROT || LENSTEP) && pair) {
         double vec[M];
         load_vec<M>(vec, p.vec, T, t, ok);
         rang = rot_angles<M>(vec, sa * p.cl[p.l_begin + l0]);
@@ -844,15 +948,16 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
     RotAngles<M> eangA, eangB;
     int pcA = -1, pcB = -1;
     bool haveA = false, haveB = false;
-    if (PROG == PROG_LEN_STEP) {
+    double kcurA = 0.0, kcurB = 0.0;  // OBS: this step's own half of the even rotations (applied after the observation)
+    if (LENSTEP) {
         double vec[M];
         load_vec<M>(vec, p.vec, T, t, ok);
         int ci;
         haveA = even_partner(p, l0, pcA, ci);
-        if (haveA) eangA = rot_angles<M>(vec, (sa + sb) * p.cl[ci]);
+        if (haveA) eangA = rot_angles<M>(vec, (OBS ? sb : sa + sb) * p.cl[ci]), kcurA = sa * p.cl[ci];
         if (pair) {
             haveB = even_partner(p, l0 + 1, pcB, ci);
-            if (haveB) eangB = rot_angles<M>(vec, (sa + sb) * p.cl[ci]);
+            if (haveB) eangB = rot_angles<M>(vec, (OBS ? sb : sa + sb) * p.cl[ci]), kcurB = sa * p.cl[ci];
         }
     }
     if (PROG == PROG_H2_CN_H2 && pair) {
@@ -863,7 +968,37 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
     pdl_wait();
     load_rows<M>(A, base, T, t, ok);
     if (pair) load_rows<M>(B, base + chan, T, t, ok);
-    if (PROG == PROG_LEN_STEP) {
+    if constexpr (OBS) {  // see the pair path above
+        double mk[M], vec[M];
+#pragma unroll
+        for (int k = 0; k < M; ++k) mk[k] = 1.0;
+        if (p.flags & F_MASK) load_vec<M>(mk, p.mask, T, t, ok);
+        load_vec<M>(vec, p.vec, T, t, ok);
+        double *osm = reinterpret_cast<double *>(xs);
+        cplx Q[M];
+#pragma unroll
+        for (int k = 0; k < M; ++k) Q[k] = c_zero();
+        if (haveA) {
+            load_rows<M>(Q, base + ((ptrdiff_t)pcA - l0) * (ptrdiff_t)chan, T, t, ok);
+            rotate_both<M>(A, Q, eangA);
+        }
+#pragma unroll
+        for (int k = 0; k < M; ++k) A[k] = c_scale(A[k], mk[k]), Q[k] = c_scale(Q[k], mk[k]);
+        obs_channel<M>(p, A, l0, b, t, mine, tl, Tc, osm);
+        if (haveA) rotate_member<M>(A, Q, rot_angles<M>(vec, kcurA));
+        if (pair) {
+#pragma unroll
+            for (int k = 0; k < M; ++k) Q[k] = c_zero();
+            if (haveB) {
+                load_rows<M>(Q, base + ((ptrdiff_t)pcB - l0) * (ptrdiff_t)chan, T, t, ok);
+                rotate_both<M>(B, Q, eangB);
+            }
+#pragma unroll
+            for (int k = 0; k < M; ++k) B[k] = c_scale(B[k], mk[k]), Q[k] = c_scale(Q[k], mk[k]);
+            obs_channel<M>(p, B, l0 + 1, b, t, mine, tl, Tc, osm);
+            if (haveB) rotate_member<M>(B, Q, rot_angles<M>(vec, kcurB));
+        }
+    } else if (LENSTEP) {
         cplx Q[M];
         if (haveA) {
             load_rows<M>(Q, base + ((ptrdiff_t)pcA - l0) * (ptrdiff_t)chan, T, t, ok);
@@ -884,7 +1019,7 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         }
     }
 
-    if (PROG == PROG_ROT_CN_ROT || PROG == PROG_LEN_STEP) {
+    if (PROG == PROG_ROT_CN_ROT || LENSTEP) {
         const RotAngles<M> &ang = rang;  // reused after the CN
         if (pair) rotate_pair<M, false>(A, B, ang);
         cn_channel<M>(A, fA, toff, toff_prev, tl, Tc, sm_scan, short_scan);
@@ -1119,7 +1254,8 @@ __global__ void k_scan_bound(const cplx *__restrict__ aggP, const cplx *__restri
 // ---------------------------------------------------------------------------------------------
 // layout conversion  reference [n][R]  <->  interleaved [n][M][T]
 // ---------------------------------------------------------------------------------------------
-__global__ void k_to_internal_c(const cplx *__restrict__ src, cplx *__restrict__ dst, int R, int M, int T, long long n)
+// src_period < n: the source holds src_period channels that are repeated (one member's g broadcast to every member of an ensemble)
+__global__ void k_to_internal_c(const cplx *__restrict__ src, cplx *__restrict__ dst, int R, int M, int T, long long n, long long src_period)
 {
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
     const int Rp = M * T;
@@ -1127,7 +1263,7 @@ __global__ void k_to_internal_c(const cplx *__restrict__ src, cplx *__restrict__
     const int k = pos / T, t = pos % T;
     const long long i = (long long)t * M + k;
     for (long long c = blockIdx.y; c < n; c += gridDim.y)
-        dst[(size_t)c * Rp + pos] = (i < R) ? src[(size_t)c * R + i] : c_zero();
+        dst[(size_t)c * Rp + pos] = (i < R) ? src[(size_t)(c % src_period) * R + i] : c_zero();
 }
 __global__ void k_from_internal_c(const cplx *__restrict__ src, cplx *__restrict__ dst, int R, int M, int T, long long n)
 {
@@ -1145,7 +1281,9 @@ __global__ void k_from_internal_c(const cplx *__restrict__ src, cplx *__restrict
 // stage 2 adds the per-channel partials in a fixed order (deterministic, no atomics).
 // partial layout per (b, l): [norm_l, r_l, z_l, h0_l, within_0..within_{nr-1}]
 // ---------------------------------------------------------------------------------------------
+#ifndef ION_MAX_RADII
 #define ION_MAX_RADII 8
+#endif
 struct ObserveParams {
     const cplx *psi;          // [batch][L][Rp]
     const double *rvec;       // [Rp] permuted r_j (0 padding)
@@ -1235,30 +1373,47 @@ __global__ void __launch_bounds__(256) k_observe(const ObserveParams p)
     }
 }
 
-// stage 2: record assembly.  One thread per simulation (L is small compared with the stage-1 work).
-__global__ void k_observe_finish(const double *__restrict__ partial, const double *__restrict__ ip, double *__restrict__ out,
-                                 int batch, int L, int n_states, int n_radii, unsigned what, double ipm, long long rec)
+// stage 2: record assembly.  One CTA per simulation; the sums over the channels are strided per thread and then combined by
+// block_sum's fixed tree, so the result does not depend on scheduling (deterministic, no atomics).
+__global__ void __launch_bounds__(256) k_observe_finish(const double *__restrict__ partial, const double *__restrict__ ip, double *__restrict__ out,
+                                                         int batch, int L, int n_states, int n_radii, unsigned what, double ipm, long long rec)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= batch) return;
+    __shared__ double sm[32 * (4 + ION_MAX_RADII)];
+    const int b = blockIdx.x, tid = threadIdx.x;
     const int np = 4 + n_radii;
+    pdl_launch_dependents();  // nobody downstream reads the record: the next step's kernels need not wait for it
+    pdl_wait();
     const double *pb = partial + (size_t)b * L * np;
     double *o = out + (size_t)b * rec;
     double sums[4 + ION_MAX_RADII];
-    for (int q = 0; q < np; ++q) sums[q] = 0.0;
-    for (int l = 0; l < L; ++l)
-        for (int q = 0; q < np; ++q) sums[q] += pb[(size_t)l * np + q];
+#pragma unroll
+    for (int q = 0; q < 4 + ION_MAX_RADII; ++q) sums[q] = 0.0;
+    for (int l = tid; l < L; l += blockDim.x) {
+#pragma unroll
+        for (int q = 0; q < 4 + ION_MAX_RADII; ++q)
+            if (q < np) sums[q] += pb[(size_t)l * np + q];
+    }
+    block_sum<4 + ION_MAX_RADII>(sums, sm, tid, blockDim.x);
     long long c = 0;
-    if (what & 1u) o[c++] = sums[0] * ipm;
-    if (what & 2u)
-        for (int s = 0; s < 2 * n_states; ++s) o[c++] = ip[(size_t)b * n_states * 2 + s];
-    if (what & 4u)
-        for (int l = 0; l < L; ++l) o[c++] = fabs(pb[(size_t)l * np] * ipm);
-    if (what & 8u) o[c++] = sums[1] * ipm;
-    if (what & 16u) o[c++] = sums[2] * ipm;
-    if (what & 32u) o[c++] = sums[3] * ipm;
-    if (what & 64u)
-        for (int q = 0; q < n_radii; ++q) o[c++] = sums[4 + q] * ipm;
+    if (what & 1u) {
+        if (tid == 0) o[c] = sums[0] * ipm;
+        c += 1;
+    }
+    if (what & 2u) {
+        for (int s = tid; s < 2 * n_states; s += blockDim.x) o[c + s] = ip[(size_t)b * n_states * 2 + s];
+        c += 2 * n_states;
+    }
+    if (what & 4u) {
+        for (int l = tid; l < L; l += blockDim.x) o[c + l] = fabs(pb[(size_t)l * np] * ipm);
+        c += L;
+    }
+    if (tid == 0) {
+        if (what & 8u) o[c++] = sums[1] * ipm;
+        if (what & 16u) o[c++] = sums[2] * ipm;
+        if (what & 32u) o[c++] = sums[3] * ipm;
+        if (what & 64u)
+            for (int q = 0; q < n_radii; ++q) o[c++] = sums[4 + q] * ipm;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -49,6 +49,25 @@ struct SlabParams {
     int nQ;                // quads in all: ceil(L / 4)
 };
 
+// Fused observation (north_star 4: reductions fused into the step): the state AFTER the mask of the step whose tail this
+// kernel applies exists only here, between the two halves of stage 3.  k_slab<true> splits stage 3 into the rotation by s_a,
+// the mask, the reductions over the CTA's interior points, and the rotation by s_b.  Every (slab, channel) / (slab, state)
+// partial sum is produced by exactly one group of G lanes (shuffle reduction) and written once; k_slab_obs_reduce adds the
+// slabs in a fixed order (deterministic, no atomics) into the buffers k_observe_finish assembles the record from.
+// Point-wise observables only (norm, norm by l, <r>, norm within radii, inner products); <z> and <H0> couple neighbouring
+// channels / rows across CTA edges and take the unfused path.
+struct SlabObs {
+    const double *rvec;       // [4][T]  permuted r_j
+    const cplx *state_rows;   // [n_states][4][T] permuted
+    const int *state_first;   // [L + 1] CSR: states of channel l
+    const int *state_order;   // [n_states]
+    double *partial;          // [batch][n_slabs][L][np], np = 4 + n_radii (k_observe's layout: norm_l, r_l, z_l = 0, h0_l = 0, within..)
+    double *ip;               // [batch][n_slabs][n_states][2]
+    double radii[ION_MAX_RADII];
+    int n_radii, n_states;
+    unsigned what;
+};
+
 // position of row r (>= 0) in the row-interleaved layout with M = 4
 ION_DEVINL int slab_pos(int r, int T) { return (r & 3) * T + (r >> 2); }
 
@@ -163,8 +182,8 @@ ION_DEVINL void slab_rot_upper(const cplx (&A)[4], cplx (&B)[4], const Trig (&an
 }
 
 // grid = (n_slabs * n_chunks, batch), block = NT (multiple of 32, NT >= G * (Qc + 2)); dynamic smem = 12 * NT cplx
-template <int NTMAX>
-__global__ void __launch_bounds__(NTMAX, NTMAX <= 288 ? 2 : 1) k_slab(const SlabParams p)
+template <bool OBS>
+__global__ void __launch_bounds__(512, 1) k_slab(const SlabParams p, const SlabObs o)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *xch = reinterpret_cast<cplx *>(smem_raw);  // [2 edges + the upper straddling pair's cos/sin][4 rows][NT]
@@ -284,14 +303,114 @@ __global__ void __launch_bounds__(NTMAX, NTMAX <= 288 ? 2 : 1) k_slab(const Slab
         if (pass == 0) {
             // ---- stage 3: even l-pairs by s_a + s_b, mask ----
             Trig ang[4];
-            slab_angles<4>(ang, v, (sa + sb) * coef(p.cl, l0), vmax);
-            slab_rot(X[0], X[1], ang);
-            slab_angles<4>(ang, v, (sa + sb) * coef(p.cl, l0 + 2), vmax);
-            slab_rot(X[2], X[3], ang);
+            if constexpr (!OBS) {
+                slab_angles<4>(ang, v, (sa + sb) * coef(p.cl, l0), vmax);
+                slab_rot(X[0], X[1], ang);
+                slab_angles<4>(ang, v, (sa + sb) * coef(p.cl, l0 + 2), vmax);
+                slab_rot(X[2], X[3], ang);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 4; ++c) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) X[c][j] = c_scale(X[c][j], mk[j]);
+                    for (int j = 0; j < 4; ++j) X[c][j] = c_scale(X[c][j], mk[j]);
+                }
+            } else {
+                // tail of step n: h1_e(s_a), mask.  X holds 2 x psi (the unnormalised Hadamard pair of stage 1), so 2 mk = mask / 2
+                // gives psi_n exactly (powers of two are exact); the other factor 1/2 (stage 5) follows the observation
+                slab_angles<4>(ang, v, sa * coef(p.cl, l0), vmax);
+                slab_rot(X[0], X[1], ang);
+                slab_angles<4>(ang, v, sa * coef(p.cl, l0 + 2), vmax);
+                slab_rot(X[2], X[3], ang);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) X[c][j] = c_scale(X[c][j], 2.0 * mk[j]);
+                }
+                {   // ---- reductions over this thread's interior points; the G lanes of a quad are consecutive lanes ----
+                    const bool q_in = q_ok && q >= q_int0 && q < q_int1;
+                    double rr[4];
+                    bool in[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int idx = 4 * g + j, r = r0 + j;
+                        in[j] = q_in && idx >= 2 && idx < 4 * G - 2 && r >= 0 && r < p.R;
+                        rr[j] = (in[j] && o.rvec) ? o.rvec[slab_pos(r, T)] : 0.0;
+                    }
+                    const int np = 4 + o.n_radii;
+                    const bool with_ip = (o.what & 2u) && o.n_states > 0;
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        const int l = l0 + c;
+                        const bool ch_ok = q_in && l < L;
+                        double n2[4], a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            // X[c] with a loop-variant c would live in local memory: select from the four channels
+                            const cplx x = c == 0 ? X[0][j] : (c == 1 ? X[1][j] : (c == 2 ? X[2][j] : X[3][j]));
+                            n2[j] = (in[j] && ch_ok) ? c_abs2(x) : 0.0;
+                            a0 += n2[j];
+                            a1 += rr[j] * n2[j];
+                        }
+                        for (int s = G >> 1; s > 0; s >>= 1) {
+                            a0 += __shfl_down_sync(0xffffffffu, a0, s);
+                            a1 += __shfl_down_sync(0xffffffffu, a1, s);
+                        }
+                        double *out = o.partial + (((size_t)b * p.n_slabs + slab) * L + (ch_ok ? l : 0)) * np;
+                        if (g == 0 && ch_ok) {
+                            out[0] = a0;
+                            out[1] = a1;
+                            out[2] = 0.0;
+                            out[3] = 0.0;
+                        }
+                        for (int k = 0; k < o.n_radii; ++k) {  // norm within radius k (mesh/data.py:419-422); uniform trip count
+                            double w = 0.0;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) w += (rr[j] <= o.radii[k]) ? n2[j] : 0.0;
+                            for (int s = G >> 1; s > 0; s >>= 1) w += __shfl_down_sync(0xffffffffu, w, s);
+                            if (g == 0 && ch_ok) out[4 + k] = w;
+                        }
+                        if (with_ip) {
+                            // inner products with the test states of this channel (mesh/meshes.py:1117-1129): sum conj(row) psi.
+                            // The trip count is made uniform over the warp (its four quads hold different channels).
+                            const int first = ch_ok ? o.state_first[l] : 0, ns = ch_ok ? o.state_first[l + 1] - first : 0;
+                            int ns_max = ns;
+#pragma unroll
+                            for (int s = 16; s > 0; s >>= 1) ns_max = max(ns_max, __shfl_xor_sync(0xffffffffu, ns_max, s));
+                            for (int si = 0; si < ns_max; ++si) {
+                                const bool have = si < ns;
+                                const int st = have ? o.state_order[first + si] : 0;
+                                double re = 0.0, im = 0.0;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    if (have && in[j]) {
+                                        const cplx x = c == 0 ? X[0][j] : (c == 1 ? X[1][j] : (c == 2 ? X[2][j] : X[3][j]));
+                                        const cplx a = o.state_rows[(size_t)st * 4 * T + slab_pos(r0 + j, T)];
+                                        re += a.x * x.x + a.y * x.y;
+                                        im += a.x * x.y - a.y * x.x;
+                                    }
+                                }
+                                for (int s = G >> 1; s > 0; s >>= 1) {
+                                    re += __shfl_down_sync(0xffffffffu, re, s);
+                                    im += __shfl_down_sync(0xffffffffu, im, s);
+                                }
+                                if (have && g == 0) {
+                                    double *oi = o.ip + (((size_t)b * p.n_slabs + slab) * o.n_states + st) * 2;
+                                    oi[0] = re;
+                                    oi[1] = im;
+                                }
+                            }
+                        }
+                    }
+                }
+                // head of step n + 1: h1_e(s_b); the remaining 1/2
+                slab_angles<4>(ang, v, sb * coef(p.cl, l0), vmax);
+                slab_rot(X[0], X[1], ang);
+                slab_angles<4>(ang, v, sb * coef(p.cl, l0 + 2), vmax);
+                slab_rot(X[2], X[3], ang);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) X[c][j] = c_scale(X[c][j], 0.5);
+                }
             }
             __syncthreads();  // everybody has read the stage-2 edges: the exchange buffer may be overwritten
         }
@@ -328,6 +447,86 @@ __global__ void __launch_bounds__(NTMAX, NTMAX <= 288 ? 2 : 1) k_slab(const Slab
         printf("SCK cta %d t %d: coef %lld pdlwait %lld loadissue %lld stage1 %lld stages2-4 %lld stage5 %lld store %lld total %lld\n", (int)blockIdx.x, tid,
                ck[1] - ck[0], ck[2] - ck[1], ck[3] - ck[2], ck[4] - ck[3], ck[5] - ck[4], ck[6] - ck[5], ck[7] - ck[6], ck[7] - ck[0]);
 #endif
+}
+
+// Record assembly for k_slab<true>: (1) one CTA per channel (and one per 64 inner-product components) adds the per-slab partial
+// sums -- thread = slab, combined by block_sum's fixed tree -> partial [batch][L][np], ip_out [batch][n_states][2] (x ipm),
+// i.e. exactly what k_observe leaves behind; (2) the CTA that finishes last for a simulation (a counter per simulation)
+// assembles the record the way k_observe_finish does.  Fixed summation orders everywhere: deterministic, no floating-point
+// atomics.  Runs on a side branch of the captured graph (engine.cu: launch_slab).  grid = (L + ceil(2 n_states / 64), batch), block = 128.
+__global__ void __launch_bounds__(128) k_slab_obs_assemble(const double *__restrict__ sp, const double *__restrict__ sip, double *__restrict__ partial,
+                                                           double *__restrict__ ip_out, unsigned *__restrict__ counter, double *__restrict__ out, int n_slabs, int L,
+                                                           int n_states, int n_radii, unsigned what, double ipm, long long rec)
+{
+    __shared__ double sm[32 * (4 + ION_MAX_RADII)];
+    __shared__ unsigned last_sm;
+    const int tid = threadIdx.x, b = blockIdx.y;
+    const int np = 4 + n_radii, n1 = L * np, n2 = 2 * n_states;
+    if ((int)blockIdx.x < L) {
+        const int l = blockIdx.x;
+        double acc[4 + ION_MAX_RADII];
+#pragma unroll
+        for (int q = 0; q < 4 + ION_MAX_RADII; ++q) acc[q] = 0.0;
+        for (int s = tid; s < n_slabs; s += blockDim.x) {
+            const double *src = sp + (((size_t)b * n_slabs + s) * L + l) * np;
+#pragma unroll
+            for (int q = 0; q < 4 + ION_MAX_RADII; ++q)
+                if (q < np) acc[q] += src[q];
+        }
+        block_sum<4 + ION_MAX_RADII>(acc, sm, tid, blockDim.x);
+        if (tid == 0) {
+#pragma unroll
+            for (int q = 0; q < 4 + ION_MAX_RADII; ++q)
+                if (q < np) partial[(size_t)b * n1 + (size_t)l * np + q] = acc[q];
+        }
+    } else {
+        // 64 components per CTA, two threads (even / odd slabs) per component, combined in a fixed order
+        const int j = ((int)blockIdx.x - L) * 64 + (tid >> 1), half = tid & 1;
+        double acc = 0.0;
+        if (j < n2)
+            for (int s = half; s < n_slabs; s += 2) acc += sip[((size_t)b * n_slabs + s) * n2 + j];
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (j < n2 && half == 0) ip_out[(size_t)b * n2 + j] = acc * ipm;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) last_sm = (atomicAdd(counter + b, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!last_sm) return;
+    if (tid == 0) counter[b] = 0u;  // ready for the next observation
+    __threadfence();
+    const volatile double *pb = partial + (size_t)b * n1;
+    const volatile double *ipb = ip_out + (size_t)b * n2;
+    double *o = out + (size_t)b * rec;
+    double sums[4 + ION_MAX_RADII];
+#pragma unroll
+    for (int q = 0; q < 4 + ION_MAX_RADII; ++q) sums[q] = 0.0;
+    for (int l = tid; l < L; l += blockDim.x) {
+#pragma unroll
+        for (int q = 0; q < 4 + ION_MAX_RADII; ++q)
+            if (q < np) sums[q] += pb[(size_t)l * np + q];
+    }
+    block_sum<4 + ION_MAX_RADII>(sums, sm, tid, blockDim.x);
+    long long c = 0;
+    if (what & 1u) {
+        if (tid == 0) o[c] = sums[0] * ipm;
+        c += 1;
+    }
+    if (what & 2u) {
+        for (int s = tid; s < n2; s += blockDim.x) o[c + s] = ipb[s];
+        c += n2;
+    }
+    if (what & 4u) {
+        for (int l = tid; l < L; l += blockDim.x) o[c + l] = fabs(pb[(size_t)l * np] * ipm);
+        c += L;
+    }
+    if (tid == 0) {
+        if (what & 8u) o[c++] = sums[1] * ipm;
+        if (what & 16u) o[c++] = sums[2] * ipm;
+        if (what & 32u) o[c++] = sums[3] * ipm;
+        if (what & 64u)
+            for (int q = 0; q < n_radii; ++q) o[c++] = sums[4 + q] * ipm;
+    }
 }
 
 }  // namespace ion

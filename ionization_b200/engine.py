@@ -171,6 +171,14 @@ class DeviceSimulation:
         nat.check(self._lib.ion_sim_write_g(self._h, nat.ptr(g)), "ion_sim_write_g")
         self.synchronize()  # g may be a temporary
 
+    def write_g_broadcast(self, g):
+        """the same wavefunction ``g`` [L, R] for every member of the ensemble (replicated on the device)"""
+        g = nat.as_c128(g)
+        if g.size != self.L * self.R:
+            raise exceptions.EngineError(f"g must have {self.L}x{self.R} elements, got shape {g.shape}")
+        nat.check(self._lib.ion_sim_write_g_broadcast(self._h, nat.ptr(g)), "ion_sim_write_g_broadcast")
+        self.synchronize()
+
     def read_g(self, out=None):
         if out is None:
             out = np.empty(self.g_shape, dtype=np.complex128)
@@ -298,7 +306,7 @@ class DeviceSimulation:
             sl = problem["state_l"] if with_states and "state_l" in problem else ()
             sr = problem["state_rows"] if with_states and "state_rows" in problem else None
             sim.set_observables(float(problem["delta_r"]), problem["r"], sl, sr, radii)
-            g0 = np.broadcast_to(np.asarray(problem["g0"], dtype=np.complex128), (batch, L, R))
+            g0 = np.asarray(problem["g0"], dtype=np.complex128).reshape(L, R)
         else:
             R = int(problem["Z"])
             sim = cls(kind, 1, R, batch=batch, device=device)
@@ -308,6 +316,6 @@ class DeviceSimulation:
             rows = problem["state_rows"] if with_states and "state_rows" in problem else None
             sl = np.zeros(len(rows), dtype=np.int64) if rows is not None else ()
             sim.set_observables(float(problem["delta_z"]), problem["z"], sl, rows, radii)
-            g0 = np.broadcast_to(np.asarray(problem["g0"], dtype=np.complex128).reshape(1, 1, R), (batch, 1, R))
-        sim.write_g(g0)
+            g0 = np.asarray(problem["g0"], dtype=np.complex128).reshape(1, R)
+        sim.write_g_broadcast(g0)
         return sim

@@ -50,12 +50,13 @@ def test_config3_2000x500_fused_graph_path_matches_oracle(gauge):
     assert launches <= 2 * n + 16, launches
 
 
-def test_config3_every_step_observed_matches_oracle():
+@pytest.mark.parametrize("gauge", ["VEL", "LEN"])
+def test_config3_every_step_observed_matches_oracle(gauge):
     """store_data_every=1 (the reference's default, sims.py:471): norm and overlaps after EVERY step of a C3 stretch"""
     from ionization_b200 import configs, engine
     from oracle import cport
 
-    p = _spread(configs.config3("VEL"), 4)
+    p = _spread(configs.config3(gauge), 4)
     start, n = 1000, 12
     what = engine.nat.OBS_NORM | engine.nat.OBS_INNER_PRODUCTS
     with engine.DeviceSimulation.from_problem(p) as sim:
@@ -154,3 +155,41 @@ def test_config5_16384x4096_four_l_block_shards(config5):
         assert not aborted and n_ex > 0
         s.close()
     assert rel_err(g, ref) < TOL
+
+
+@pytest.mark.parametrize("name", ["sh_len_so_datastores_120x12", "sh_vel_so_datastores_120x12", "c1_sh_len_so_500x50", "c1_sh_vel_so_500x50"])
+def test_fused_observation_equals_separate_observation(name, monkeypatch):
+    """north_star (4): on the fused schedule the reductions ride inside the step kernels (k_slab<OBS>, k_unit<LEN_STEP_OBS>).
+    Every record must equal the one k_observe computes from the finished state of the same step on the single-sweep schedule."""
+    from conftest import load_golden
+    from ionization_b200 import engine
+
+    p = load_golden(name)
+    nat = engine.nat
+    what = nat.OBS_NORM | nat.OBS_INNER_PRODUCTS | nat.OBS_NORM_BY_L | nat.OBS_R | nat.OBS_NORM_WITHIN
+    radii = [float(p["r"][len(p["r"]) // 5]), float(p["r"][len(p["r"]) // 2])]
+    n = min(len(p["taus"]), 150)
+    # sparse and dense patterns, incl. consecutive observed steps and an observed last step
+    pattern = np.zeros(n, dtype=np.uint8)
+    pattern[[i for i in (0, 1, 2, 7, 8, 30, 63, 64, 65, n - 1) if i < n]] = 1
+    out = {}
+    for mode in ("fused", "separate"):
+        if mode == "separate":
+            monkeypatch.setenv("ION_NO_FUSED_OBS", "1")
+        with engine.DeviceSimulation.from_problem(p, radii=radii) as sim:
+            before = sim.launch_count
+            recs = sim.run(p["taus"][:n], p["fields"][:n], pattern, what)[:, 0]
+            out[mode] = (recs, sim.read_g()[0], sim.launch_count - before)
+        dense = np.ones(n, dtype=np.uint8)
+        with engine.DeviceSimulation.from_problem(p, radii=radii) as sim:
+            out[mode + "_dense"] = (sim.run(p["taus"][:n], p["fields"][:n], dense, what)[:, 0], sim.read_g()[0], 0)
+    monkeypatch.delenv("ION_NO_FUSED_OBS")
+    for a, b in (("fused", "separate"), ("fused_dense", "separate_dense")):
+        ra, ga, _ = out[a]
+        rb, gb, _ = out[b]
+        assert ra.shape == rb.shape
+        assert np.max(np.abs(ra - rb)) < 1e-12 * max(1.0, np.max(np.abs(rb))), (a, np.max(np.abs(ra - rb)))
+        assert rel_err(ga, gb) < 1e-12
+    assert rel_err(out["fused"][1], p["g_final"]) < TOL if n == len(p["taus"]) else True
+    # the observed steps stayed on the fused schedule: far fewer launches than the single-sweep schedule needs
+    assert out["fused"][2] < out["separate"][2]
