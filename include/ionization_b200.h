@@ -188,6 +188,10 @@ int ion_sim_attach_peer(ion_sim_t *sim, int side /* 0: lower neighbour, 1: upper
 int ion_sim_exchange_halos(ion_sim_t *sim);
 /* build the LU factors for tau now (everything that allocates), so that later steps only launch kernels */
 int ion_sim_prepare(ion_sim_t *sim, double tau);
+/* size every buffer a later ion_sim_step / ion_sim_run of n_steps steps with n_records observations of `what` needs, now.
+ * Linked shards must not allocate or free between hand-shakes (cudaFree waits for the device to go idle, which it never does
+ * while a neighbour's exchange kernel is waiting for this shard): call ion_sim_prepare and ion_sim_reserve on every shard first. */
+int ion_sim_reserve(ion_sim_t *sim, int64_t n_steps, int64_t n_records, uint32_t what);
 /* exchanges completed so far; aborted != 0: a hand-shake timed out (a neighbour never arrived), the state is invalid */
 int ion_sim_halo_status(ion_sim_t *sim, int64_t *exchanges_done, int *aborted);
 

@@ -7,6 +7,7 @@ Public surface (mirrors ``ionization`` for this path; see DESIGN.md / INTEGRATIO
     ionization_b200.states      hydrogen / 1-D states (host-side inputs)
     ionization_b200.engine      the CUDA engine behind the C-ABI (include/ionization_b200.h)
     ionization_b200.parallel    one-process-per-GPU ensembles and l-block sharding (torch.distributed)
+    ionization_b200.scan        ParameterScan container (ionization/analysis.py) and the scan runner sharded over GPUs
 
 The compute path is hand-written sm_100a CUDA behind a C-ABI shared library; there is no CPU fallback.
 """

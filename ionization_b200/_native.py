@@ -72,6 +72,7 @@ SIGNATURES = {
     "ion_sim_attach_peer": (_i32, [_vp, _i32, _vp, _i64, _i32]),
     "ion_sim_exchange_halos": (_i32, [_vp]),
     "ion_sim_prepare": (_i32, [_vp, _f64]),
+    "ion_sim_reserve": (_i32, [_vp, _i64, _i64, _u32]),
     "ion_sim_halo_status": (_i32, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_i32)]),
     "ion_sim_num_phases": (_i32, [_vp]),
     "ion_sim_phase_needs_halo": (_i32, [_vp, _i32]),

@@ -1746,6 +1746,19 @@ int ion_sim_attach_peer(ion_sim_t *s, int side, const void *blob, int64_t blob_b
     unsigned long long *pblock = nullptr;
     if (same_process) {
         pblock = reinterpret_cast<unsigned long long *>((uintptr_t)b.local_halo);
+        // several shards of ONE process on different GPUs (mesh API: SphericalHarmonicSpecification(devices=[...])): the
+        // neighbour's halo block is dereferenced by this device's kernels, which needs peer access between the two devices
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, pblock) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device != s->device) {
+            int can = 0;
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, s->device, pa.device));
+            if (!can) return fail(ION_ENOTSUP, "devices " + std::to_string(s->device) + " and " + std::to_string(pa.device) + " cannot access each other's memory (no NVLink / PCIe peer path)");
+            cudaError_t e = cudaDeviceEnablePeerAccess(pa.device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) return fail(ION_ECUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        } else {
+            cudaGetLastError();
+        }
     } else {
         void *q = nullptr;
         CUDA_TRY(cudaIpcOpenMemHandle(&q, b.halo, cudaIpcMemLazyEnablePeerAccess));
@@ -1776,6 +1789,45 @@ int ion_sim_prepare(ion_sim_t *s, double tau)
     if (int rc = ensure_factor(s, tau)) return rc;
     if (s->S > 1 || s->program == ION_SH_LEN_ADI)
         if (int rc = ensure_second_buffer(s)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return ION_OK;
+}
+
+int ion_sim_reserve(ion_sim_t *s, int64_t n_steps, int64_t n_records, uint32_t what)
+{
+    if (!s) return fail(ION_EINVAL, "sim is NULL");
+    if (n_steps < 0 || n_records < 0) return fail(ION_EINVAL, "negative count");
+    CUDA_TRY(cudaSetDevice(s->device));
+    // everything ion_sim_step / ion_sim_run would (re)allocate for a call of this size.  cudaFree waits for the device to go
+    // idle, which never happens while another shard's halo kernel is waiting for THIS shard's kernels: linked shards must not
+    // (re)allocate between hand-shakes, so their buffers are sized up front.
+    const size_t need = (size_t)(n_steps + 2) * s->batch;
+    if (need > s->scal_cap) {
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if (int rc = dev_alloc(&s->scal, need)) return rc;
+        s->scal_cap = need;
+    }
+    for (int k = 0; k < 2; ++k) {
+        if (need > s->scal_host_cap[k]) {
+            if (s->scal_ev[k]) CUDA_TRY(cudaEventSynchronize(s->scal_ev[k]));
+            if (s->scal_host[k]) cudaFreeHost(s->scal_host[k]);
+            s->scal_host[k] = nullptr;
+            s->scal_host_cap[k] = 0;
+            CUDA_TRY(cudaMallocHost((void **)&s->scal_host[k], need * sizeof(double)));
+            s->scal_host_cap[k] = need;
+        }
+    }
+    if (!s->scal_chunk)
+        if (int rc = dev_alloc(&s->scal_chunk, (size_t)(GRAPH_CHUNK + 2) * s->batch)) return rc;
+    if (n_records > 0) {
+        if (int rc = ensure_observe_buffers(s, (size_t)n_records, what)) return rc;
+        const size_t rec = (size_t)ion_sim_observation_size(s, what) * s->batch;
+        if (s->obs_chunk_cap < (size_t)GRAPH_CHUNK * rec) {
+            s->invalidate_graphs();
+            if (int rc = dev_alloc(&s->obs_chunk, (size_t)GRAPH_CHUNK * rec)) return rc;
+            s->obs_chunk_cap = (size_t)GRAPH_CHUNK * rec;
+        }
+    }
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return ION_OK;
 }

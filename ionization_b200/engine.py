@@ -256,6 +256,10 @@ class DeviceSimulation:
     def prepare(self, tau: float):
         nat.check(self._lib.ion_sim_prepare(self._h, float(tau)), "ion_sim_prepare")
 
+    def reserve(self, n_steps: int, n_records: int = 0, what: int = 0):
+        """size the buffers of a later step / run call now (linked shards must not allocate between hand-shakes)"""
+        nat.check(self._lib.ion_sim_reserve(self._h, int(n_steps), int(n_records), int(what)), "ion_sim_reserve")
+
     def halo_status(self):
         n, ab = ctypes.c_int64(0), ctypes.c_int32(0)
         nat.check(self._lib.ion_sim_halo_status(self._h, ctypes.byref(n), ctypes.byref(ab)), "ion_sim_halo_status")

@@ -13,6 +13,7 @@ from .data import (  # noqa: F401
     RExpectationValue,
     TotalEnergyExpectationValue,
     ZExpectationValue,
+    DirectionalRadialProbabilityCurrent,
     DEFAULT_DATASTORE_TYPES,
     DATA_NAME_TO_DATASTORE_TYPE,
     DATASTORE_TYPE_TO_DATA_NAMES,
@@ -33,4 +34,5 @@ from .sims import (  # noqa: F401
     SphericalHarmonicSimulation,
     SphericalHarmonicSpecification,
 )
+from .snapshots import Snapshot, SphericalHarmonicSnapshot  # noqa: F401
 from .ensemble import MeshEnsemble, run_ensemble  # noqa: F401

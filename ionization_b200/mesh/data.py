@@ -35,6 +35,7 @@ DATA_NAME_TO_DATASTORE_TYPE = {}
 
 class Datastore:
     observables = 0  # bit mask of engine observables this datastore consumes
+    needs_mesh = False  # True: store() reads sim.mesh (host-side analysis); the run loop then stops at every data time
 
     def init(self, sim):
         self.sim = sim
@@ -275,6 +276,46 @@ class NormBySphericalHarmonic(Datastore):
 
 
 DATA_NAME_TO_DATASTORE_TYPE.update({"norm_by_l": NormBySphericalHarmonic, "norm_by_sph_harm": NormBySphericalHarmonic})
+
+class DirectionalRadialProbabilityCurrent(Datastore):
+    """data.py:467-531: the radial probability current as a function of radius, integrated over the upper (z > 0) and the lower
+    hemisphere.  Host-side analysis on the (r, theta) reconstruction of the synchronised wavefunction at the data times."""
+
+    needs_mesh = True
+
+    def init(self, sim):
+        self.radial_probability_current__pos_z = np.zeros((sim.data_time_steps, sim.spec.r_points), dtype=np.float64) * np.nan
+        self.radial_probability_current__neg_z = np.zeros((sim.data_time_steps, sim.spec.r_points), dtype=np.float64) * np.nan
+        theta = sim.mesh.theta_calc
+        self.d_theta = np.abs(theta[1] - theta[0])
+        self.sin_theta = np.sin(theta)
+        self.mask = theta <= np.pi / 2
+        super().init(sim)
+
+    def store(self, record, idx):
+        mesh = self.sim.mesh
+        radial_current_density = mesh.get_radial_probability_current_density_mesh__spatial()
+        integrand = radial_current_density * self.sin_theta * self.d_theta * (2 * np.pi)  # sin(theta) d_theta, two pi from phi
+        self.radial_probability_current__pos_z[idx] = np.sum(integrand[:, self.mask], axis=1) * (mesh.r ** 2)
+        self.radial_probability_current__neg_z[idx] = np.sum(integrand[:, ~self.mask], axis=1) * (mesh.r ** 2)
+
+    def attach(self):
+        self.sim.data.radial_probability_current__pos_z = self.radial_probability_current__pos_z
+        self.sim.data.radial_probability_current__neg_z = self.radial_probability_current__neg_z
+
+    def radial_probability_current__total(self):
+        return self.radial_probability_current__pos_z + self.radial_probability_current__neg_z
+
+    def __sizeof__(self):
+        return self.radial_probability_current__pos_z.nbytes + self.radial_probability_current__neg_z.nbytes + super().__sizeof__()
+
+
+_link(DirectionalRadialProbabilityCurrent, "radial_probability_current__total")
+DATA_NAME_TO_DATASTORE_TYPE.update({
+    "radial_probability_current__pos_z": DirectionalRadialProbabilityCurrent,
+    "radial_probability_current__neg_z": DirectionalRadialProbabilityCurrent,
+    "radial_probability_current__total": DirectionalRadialProbabilityCurrent,
+})
 
 DATASTORE_TYPE_TO_DATA_NAMES = collections.defaultdict(set)
 for _data_name, _datastore_type in DATA_NAME_TO_DATASTORE_TYPE.items():

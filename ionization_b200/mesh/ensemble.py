@@ -58,6 +58,10 @@ class MeshEnsemble:
             why = _compatible(specs[0], s)
             if why:
                 raise exceptions.UnsupportedConfiguration(f"ensemble members must share the mesh and time grid: {why}")
+        for sp in specs:
+            if sp.snapshot_times or sp.snapshot_indices or any(getattr(ds, "needs_mesh", False) for ds in sp.datastores):
+                raise exceptions.UnsupportedConfiguration("snapshots and mesh-analysing datastores need the wavefunction on the host at intermediate times; "
+                                                          "run such members one by one (spec.to_sim().run())")
         self.device = device
         specs[0].device = device
         first = specs[0].to_sim()
@@ -163,5 +167,11 @@ class MeshEnsemble:
         return self.sims
 
 
-def run_ensemble(specs, device=0):
-    return MeshEnsemble(specs, device=device).run()
+def run_ensemble(specs, device=0, devices=None):
+    """``devices``: split the members into contiguous blocks, one batched device run per GPU, concurrently
+    (ionization_b200.scan.run_scan; under torchrun the ranks take the blocks instead)"""
+    if devices is not None and len(devices) > 1:
+        from .. import scan
+
+        return scan.run_scan(specs, devices=devices, keep_mesh=True)
+    return MeshEnsemble(specs, device=devices[0] if devices else device).run()

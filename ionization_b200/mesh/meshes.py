@@ -99,6 +99,13 @@ class QuantumMesh:
             return self.get_g_for_state(state_or_mesh)
         return state_or_mesh
 
+    def get_g_with_states_removed(self, states_to_remove, g=None):
+        """g - sum_s <s|g> |s>  (meshes.py:163-193); always acts on a copy"""
+        g = np.array(self.state_to_g(g), dtype=np.complex128, copy=True)
+        for state in states_to_remove:
+            g -= self.inner_product(state, g) * self.get_g_for_state(state)
+        return g
+
     def _observe(self, what):
         """device reductions of the current wavefunction -> dict"""
         eng = self.engine
@@ -326,6 +333,61 @@ class SphericalHarmonicMesh(QuantumMesh):
             return sum(np.sum(np.conj(self.get_radial_g_for_state(s)) * g[s.l, :]) for s in a) * self.inner_product_multiplier
         return super().inner_product(a, b)
 
+    # ---- spatial (r, theta) reconstruction and the analysis built on it: host-side numpy on the synchronised g, evaluated at
+    # ---- snapshot / data times only (meshes.py:1456-1513; not part of the per-step path)
+    @property
+    def theta_calc(self):
+        return np.linspace(0, u.pi, self.theta_points)
+
+    @property
+    def _sph_harm_l_theta_calc_mesh(self):
+        """Y_l^0(theta) on (l, theta_calc): sqrt((2l+1)/(4 pi)) P_l(cos theta) (meshes.py:1485-1489 via scipy's sph_harm there)"""
+        if getattr(self, "_ylt_cache", None) is None:
+            import scipy.special as special
+
+            l_mesh, theta_mesh = np.meshgrid(self.l, self.theta_calc, indexing="ij")
+            self._ylt_cache = (np.sqrt((2 * l_mesh + 1) / (4 * u.pi)) * special.eval_legendre(l_mesh, np.cos(theta_mesh))).astype(np.complex128)
+        return self._ylt_cache
+
+    def reconstruct_spatial_mesh__calc(self, mesh):
+        """(l, r) -> (r, theta)  (meshes.py:1498-1503)"""
+        return np.einsum("lr,lt->rt", mesh, self._sph_harm_l_theta_calc_mesh)
+
+    @property
+    def space_g_calc(self):
+        return self.reconstruct_spatial_mesh__calc(self.g)
+
+    def get_radial_probability_current_density_mesh__spatial(self):
+        """Im(conj(g) D_r g) on the (r, theta) mesh with the antisymmetric radial difference operator D_r
+        (meshes.py:1358-1370; mesh_operators.py:1106-1127).  The reference's own call omits the mesh argument of
+        r_probability_current__spatial (meshes.py:1359) and therefore raises TypeError there; this is its evident intent."""
+        off = self.operators.r_probability_current_offdiagonal(self)  # [R - 1], couples r_j and r_{j+1} at fixed theta
+        g_spatial = self.space_g_calc
+        grad = np.zeros_like(g_spatial)
+        grad[:-1, :] += off[:, None] * g_spatial[1:, :]
+        grad[1:, :] -= off[:, None] * g_spatial[:-1, :]
+        return np.imag(np.conj(g_spatial) * grad)
+
+    def inner_product_with_plane_waves(self, thetas, wavenumbers, g=None):
+        """<plane wave(theta, k) | g> for the Cartesian product of thetas and wavenumbers (meshes.py:1138-1190):
+        sum_{l, r} sqrt(2/pi) r (-i^{l mod 4}) dr g[l, r] Y_l^0(theta) j_l(k r).  The reference evaluates the double loop over
+        (theta, k) in Python; here the sum over r is done once per wavenumber and the sum over l is one matrix product."""
+        import scipy.special as special
+
+        if g is None:
+            g = self.g
+        g = np.asarray(g, dtype=np.complex128)
+        l_mesh = self.l_mesh
+        multiplier = np.sqrt(2 / u.pi) * self.g_factor * (-(1j ** (l_mesh % 4))) * self.inner_product_multiplier * g
+        thetas, wavenumbers = np.array(thetas), np.array(wavenumbers)
+        theta_mesh, wavenumber_mesh = np.meshgrid(thetas, wavenumbers, indexing="ij")
+        lt, tt = np.meshgrid(self.l, thetas, indexing="ij")
+        y_lt = np.sqrt((2 * lt + 1) / (4 * u.pi)) * special.eval_legendre(lt, np.cos(tt))  # Y_l^0(theta), [L, n_theta]
+        b_lk = np.empty((len(self.l), len(wavenumbers)), dtype=np.complex128)
+        for jj, k in enumerate(wavenumbers):
+            b_lk[:, jj] = np.sum(multiplier * special.spherical_jn(l_mesh, np.real(k * self.r_mesh)), axis=1)
+        return theta_mesh, wavenumber_mesh, y_lt.T @ b_lk
+
     def norm_by_l(self, state=None):
         """meshes.py:1133-1136"""
         if state is None:
@@ -359,9 +421,36 @@ class SphericalHarmonicMesh(QuantumMesh):
                 )
         return out
 
+    def _build_sharded_engine(self, devices):
+        """l-block shards on several GPUs of this process (mesh/sharded.py)"""
+        from .. import coefficients as C
+        from . import sharded
+
+        sim, spec = self.sim, self.spec
+        if sim._program not in ("sh_len_so", "sh_vel_so"):
+            raise exceptions.UnsupportedConfiguration("devices=[...]: l-block sharding is available for the split-operator SphericalHarmonic programs")
+        hd, ho = self.operators.hamiltonian_vectors(self)
+        flat = sim._flat_states
+        problem = dict(
+            kind=sim._program, L=spec.l_bound, R=spec.r_points, r=self.r, delta_r=self.delta_r, h_diag=hd, h_off=ho, g0=self.g,
+            mask=sim._mask_vector if sim._mask_vector is not None else np.ones(spec.r_points),
+            state_l=np.array([s.l for s in flat], dtype=np.int64), state_rows=np.array([self.get_radial_g_for_state(s) for s in flat]) if flat else None,
+        )
+        if sim._program == "sh_vel_so":
+            problem["c_l"], problem["f1_l"], problem["y_j"], problem["z_j"] = C.sh_vel_coupling(self.r, self.delta_r, spec.l_bound, spec.test_charge, spec.test_mass)
+        else:
+            problem["c_l"], problem["x_j"] = C.sh_len_coupling(self.r, spec.l_bound, spec.test_charge)
+        eng = sharded.ShardedEngine(problem, devices, radii=sim._radii)
+        if sim._mask_vector is None:
+            eng.set_mask(None)
+        return eng
+
     def _build_engine(self):
         sim, spec = self.sim, self.spec
         L, R = self.mesh_shape
+        devices = getattr(spec, "devices", None)
+        if devices is not None and len(devices) > 1:
+            return self._build_sharded_engine(devices)
         eng = _engine.DeviceSimulation(sim._program, L, R, batch=1, device=sim.device)
         hd, ho = self.operators.hamiltonian_vectors(self)
         eng.set_hamiltonian(hd, ho)

@@ -56,6 +56,19 @@ class SphericalHarmonicLengthGaugeOperators(MeshOperators):
     beta = staticmethod(C.sh_beta)
     c_l = staticmethod(C.sh_c_l)
 
+    @staticmethod
+    def gamma(j):
+        """for the radial probability current (mesh_operators.py:849-851)"""
+        return 1 / ((np.asarray(j, dtype=np.float64) ** 2) - 0.25)
+
+    def r_probability_current_offdiagonal(self, mesh):
+        """the super-diagonal of the antisymmetric radial-current operator along r, [r_points - 1]: hbar / (2 m dr^3) gamma(j),
+        j = 1 .. r_points - 1; the sub-diagonal is its negative (mesh_operators.py:1106-1127)"""
+        from .. import units as u
+
+        pre = u.hbar / (2 * mesh.spec.test_mass * (mesh.delta_r ** 3))
+        return pre * self.gamma(np.arange(1, mesh.spec.r_points))
+
     def hamiltonian_vectors(self, mesh):
         spec = mesh.spec
         V = spec.internal_potential(r=mesh.r, test_charge=spec.test_charge)

@@ -24,7 +24,7 @@ from .. import exceptions, potentials, states
 from .. import units as u
 from ..core import Status
 from . import data as data_mod
-from . import evolution_methods, meshes
+from . import evolution_methods, meshes, snapshots
 from . import operators as mesh_operators
 
 logger = logging.getLogger(__name__)
@@ -100,6 +100,7 @@ class MeshSpecification(_Beet):
         snapshot_kwargs=None,
         datastores=None,
         device=0,
+        devices=None,
         file_name=None,
         **kwargs,
     ):
@@ -131,7 +132,7 @@ class MeshSpecification(_Beet):
         self.store_data_every = int(store_data_every)
         self.snapshot_times = set(snapshot_times)
         self.snapshot_indices = set(snapshot_indices)
-        self.snapshot_type = snapshot_type
+        self.snapshot_type = snapshot_type if snapshot_type is not None else snapshots.Snapshot  # sims.py:565-567
         self.snapshot_kwargs = snapshot_kwargs or dict()
         if datastores is None:
             datastores = [ds_type() for ds_type in data_mod.DEFAULT_DATASTORE_TYPES]
@@ -139,7 +140,10 @@ class MeshSpecification(_Beet):
         self.datastore_types = tuple(sorted(set(ds.__class__ for ds in self.datastores), key=lambda ds: ds.__name__))
         if len(self.datastores) != len(self.datastore_types):
             raise exceptions.DuplicateDatastores("Cannot duplicate datastores")
-        self.device = int(device)
+        # devices=[d0, d1, ...]: ONE simulation l-block sharded over several GPUs of this process (mesh/sharded.py); device: the GPU
+        # of an unsharded simulation
+        self.devices = None if devices is None else [int(d) for d in devices]
+        self.device = int(device) if self.devices is None else self.devices[0]
 
     def to_sim(self):
         return self.simulation_type(self)
@@ -287,8 +291,18 @@ class MeshSimulation(_Beet):
         self._what |= nat.OBS_NORM  # check() needs it
         self._host_field_cache = None
 
+        # snapshot times from the two ways of entering them in the spec, by time or by index (sims.py:104-114)
         self.snapshot_times = set()
+        self._snapshot_indices = set()
+        for t in spec.snapshot_times:
+            idx = int(np.argmin(np.abs(self.times - t)))  # simulacra.utils.find_nearest_entry
+            self.snapshot_times.add(self.times[idx])
+            self._snapshot_indices.add(idx)
+        for idx in spec.snapshot_indices:
+            self.snapshot_times.add(self.times[idx])
+            self._snapshot_indices.add(int(idx) % self.time_steps)
         self.snapshots = dict()
+        self._needs_mesh = any(ds.needs_mesh for ds in self.datastores_by_type.values())
         self.warnings = collections.defaultdict(list)
 
     # ---- helpers -----------------------------------------------------------------------------------
@@ -317,6 +331,23 @@ class MeshSimulation(_Beet):
     @property
     def percent_completed(self):
         return round(100 * self.time_index / (self.time_steps - 1), 2)
+
+    @property
+    def bound_states(self):
+        """sims.py:362-364"""
+        yield from (s for s in self.spec.test_states if s.bound)
+
+    @property
+    def free_states(self):
+        """sims.py:366-368"""
+        yield from (s for s in self.spec.test_states if not s.bound)
+
+    def take_snapshot(self):
+        """sims.py:242-253"""
+        snapshot = self.spec.snapshot_type(self, self.time_index, **self.spec.snapshot_kwargs)
+        snapshot.take_snapshot()
+        self.snapshots[self.time_index] = snapshot
+        logger.info(f"Stored {snapshot.__class__.__name__} for {self} at time index {self.time_index} (t = {self.time / u.asec:.3f} as)")
 
     def _split_record(self, rec, what):
         """engine record (include/ionization_b200.h: ion_sim_observation_size) -> dict"""
@@ -437,6 +468,8 @@ class MeshSimulation(_Beet):
             if self.data_mask[self.time_index]:  # same truth values as `self.time in self.data_times` (:290), O(1)
                 self.store_data()
                 self.check()
+            if self.time_index in self._snapshot_indices:  # `self.time in self.snapshot_times` (sims.py:296-297)
+                self.take_snapshot()
             if callback is not None:
                 callback(self)
             if self.data_mask[self.time_index]:
@@ -452,6 +485,13 @@ class MeshSimulation(_Beet):
                 # device-resident stretch up to the end (or the next checkpoint opportunity)
                 n0 = self.time_index
                 n1 = last if chunk_limit is None else min(last, n0 + chunk_limit)
+                # the host needs the wavefunction at snapshot times, and at every data time when a datastore analyses the mesh itself:
+                # the stretch ends there and the loop head above does the work
+                stops = [i for i in self._snapshot_indices if i > n0]
+                if self._needs_mesh:
+                    stops += [int(i) for i in self.data_indices if i > n0]
+                if stops:
+                    n1 = min(n1, min(stops))
                 obs = self.data_mask[n0 + 1 : n1 + 1].astype(np.uint8)
                 obs[-1] = 0  # the final index of the stretch is stored by the loop head above
                 recs = self._advance(n0, n1, obs)

@@ -116,9 +116,7 @@ class LocalExchanger:
 class ShardedSimulation:
     """The shard of ``problem`` (a dict of hot-path inputs, keys as in tests/golden/*.npz) owned by ``rank``."""
 
-    def __init__(self, problem, rank: int, world_size: int, device: int = 0, use_torch_stream: bool = True):
-        import torch
-
+    def __init__(self, problem, rank: int, world_size: int, device: int = 0, use_torch_stream: bool = True, radii=()):
         kind = str(problem["kind"])
         if kind not in ("sh_len_so", "sh_vel_so"):
             raise exceptions.UnsupportedConfiguration("l-block sharding: split-operator SphericalHarmonic programs only")
@@ -129,6 +127,8 @@ class ShardedSimulation:
         eng = _engine.DeviceSimulation(kind, self.L, R, batch=1, device=device, L_total=L_total, l_begin=self.l_begin)
         self.engine = eng
         if use_torch_stream:
+            import torch
+
             self.stream = torch.cuda.Stream(device=device)
             eng.set_stream(self.stream.cuda_stream)
         else:
@@ -142,11 +142,14 @@ class ShardedSimulation:
         eng.set_mask(problem["mask"])
         sl = np.asarray(problem["state_l"]) if "state_l" in problem else np.zeros(0, dtype=np.int64)
         rows = problem["state_rows"] if len(sl) else None
-        eng.set_observables(float(problem["delta_r"]), problem["r"], sl, rows, ())
+        eng.set_observables(float(problem["delta_r"]), problem["r"], sl, rows, radii)
         eng.write_g(np.asarray(problem["g0"])[self.l_begin : self.l_begin + self.L].reshape(1, self.L, R))
         bufs = [eng.halo_buffer(w) for w in range(4)]
-        mk = lambda pb: None if pb[0] is None else device_tensor(pb[0], pb[1], device)
-        self.send_lo, self.send_hi, self.recv_lo, self.recv_hi = (mk(b) for b in bufs)
+        if use_torch_stream:  # torch views of the boundary buffers: only the NCCL / in-process copy transports need them
+            mk = lambda pb: None if pb[0] is None else device_tensor(pb[0], pb[1], device)
+            self.send_lo, self.send_hi, self.recv_lo, self.recv_hi = (mk(b) for b in bufs)
+        else:
+            self._halo_bufs = bufs
         self.n_phases = eng.num_phases
         self.halo_phases = [p for p in range(self.n_phases) if eng.phase_needs_halo(p)]
 
@@ -180,6 +183,16 @@ class ShardedSimulation:
         """advance len(taus) steps with the device-resident loop (fused kernels, CUDA graphs, halo exchange by the engine's
         own kernels over peer memory).  Asynchronous; every shard must be advanced by the same number of steps."""
         self.engine.step(np.atleast_1d(taus), np.atleast_1d(fields))
+
+    def __getattr__(self, name):
+        # lazily created torch views for shards built without a torch stream (tests drive LocalExchanger with them)
+        if name in ("send_lo", "send_hi", "recv_lo", "recv_hi") and "_halo_bufs" in self.__dict__:
+            mk = lambda pb: None if pb[0] is None else device_tensor(pb[0], pb[1], self.device)
+            vals = [mk(b) for b in self._halo_bufs]
+            for k, v in zip(("send_lo", "send_hi", "recv_lo", "recv_hi"), vals):
+                self.__dict__[k] = v
+            return self.__dict__[name]
+        raise AttributeError(name)
 
     def make_exchanger(self, group=None) -> HaloExchanger:
         return HaloExchanger(self.rank, self.world, self.send_lo, self.send_hi, self.recv_lo, self.recv_hi, group)

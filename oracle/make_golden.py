@@ -264,6 +264,97 @@ def dump_line(name, kind, spec_kwargs, *, store=1):
     return d
 
 
+def dump_sh_analysis(name, spec_kwargs, snapshot_indices=(20, 60), theta_points=24):
+    """SphericalHarmonicSnapshot plane-wave overlaps (snapshots.py:37-80, meshes.py:1138-1190) taken by the
+    reference's own run loop, and the radial probability current density of the final state (meshes.py:1358-1370,
+    mesh_operators.py:1106-1127, data.py:496-511).  The reference's DirectionalRadialProbabilityCurrent datastore cannot be
+    attached (its store() takes no arguments and meshes.py:1359 omits the mesh argument), so the same statements are
+    evaluated here on the reference's objects with the mesh passed explicitly."""
+    t0 = time.perf_counter()
+    snap_kw = dict(plane_wave_overlap__max_wavenumber=20 * u.per_nm, plane_wave_overlap__wavenumber_points=12, plane_wave_overlap__theta_points=9)
+    sim = ion.mesh.SphericalHarmonicSpecification(
+        name, operators=ion.mesh.SphericalHarmonicLengthGaugeOperators(), evolution_method=ion.mesh.SplitInteractionOperator(), store_data_every=20,
+        theta_points=theta_points, **spec_kwargs,
+    ).to_sim()
+    d = dict(kind="sh_len_so", **_sh_inputs(sim), **_states_sh(sim))
+    d["fields"] = _sh_fields(sim, "sh_len_so")
+    # The reference's SphericalHarmonicSnapshot cannot take its free-only overlaps: snapshots.py:73 calls
+    # get_g_with_states_removed(bound_states) without the required g (meshes.py:163-165) and raises TypeError.  The same
+    # statements (snapshots.py:59-80) are evaluated here on the reference's mesh with g passed, at the snapshot indices.
+    thetas = np.linspace(0, u.twopi, snap_kw["plane_wave_overlap__theta_points"])
+    wavenumbers = np.delete(np.linspace(0, snap_kw["plane_wave_overlap__max_wavenumber"], snap_kw["plane_wave_overlap__wavenumber_points"] + 1), 0)
+    taken = {}
+
+    def cb(s):
+        if s.time_index in snapshot_indices:
+            m = s.mesh
+            g_free = m.get_g_with_states_removed(s.bound_states, m.g)
+            taken[s.time_index] = (m.norm(), m.inner_product_with_plane_waves(thetas, wavenumbers, g=None)[2],
+                                   m.inner_product_with_plane_waves(thetas, wavenumbers, g=g_free)[2])
+
+    sim.run(callback=cb)
+    d.update(_outputs(sim))
+    d["snapshot_indices"] = np.array(sorted(taken))
+    d["snapshot_thetas"], d["snapshot_wavenumbers"] = thetas, wavenumbers
+    for idx, (nrm, ip_all, ip_free) in taken.items():
+        d[f"snapshot_{idx}_norm"] = nrm
+        d[f"snapshot_{idx}_inner_product_with_plane_waves"] = ip_all
+        d[f"snapshot_{idx}_inner_product_with_plane_waves__free_only"] = ip_free
+    mesh = sim.mesh
+    op = sim.spec.operators.r_probability_current__spatial(mesh)
+    g_spatial = mesh.space_g_calc
+    grad = np.reshape(op.matrix.dot(g_spatial.flatten("F")), g_spatial.shape, "F")
+    density = np.imag(np.conj(g_spatial) * grad)
+    theta = mesh.theta_calc
+    integrand = density * np.sin(theta) * np.abs(theta[1] - theta[0]) * u.twopi
+    up = theta <= u.pi / 2
+    d["theta_points"] = theta_points
+    d["radial_current_density_final"] = density
+    d["radial_current_pos_z_final"] = np.sum(integrand[:, up], axis=1) * mesh.r ** 2
+    d["radial_current_neg_z_final"] = np.sum(integrand[:, ~up], axis=1) * mesh.r ** 2
+    d["snapshot_kwargs_max_wavenumber"] = snap_kw["plane_wave_overlap__max_wavenumber"]
+    d.update({f"const_{k}": v for k, v in CONSTANTS.items()})
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **d)
+    print(f"{name}: analysis fixture, snapshots at {sorted(taken)} ({time.perf_counter() - t0:.1f}s, {os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
+    return d
+
+
+def dump_line_datastores(name, kind, spec_kwargs):
+    """LineMesh with the expectation-value datastores (<z> and the energies on a line mesh were untested)"""
+    ops, method = {
+        "line_len_cn": (ion.mesh.LineLengthGaugeOperators, ion.mesh.AlternatingDirectionImplicit),
+        "line_len_so": (ion.mesh.LineLengthGaugeOperators, ion.mesh.SplitInteractionOperator),
+    }[kind]
+    D = ion.mesh
+    sim = ion.mesh.LineSpecification(
+        name, operators=ops(), evolution_method=method(), store_data_every=5,
+        datastores=[D.Fields(), D.Norm(), D.InnerProducts(), D.InternalEnergyExpectationValue()], **spec_kwargs,  # total energy: total_hamiltonian is a tuple on a line mesh (mesh_operators.py:271-298), the reference cannot evaluate it
+    ).to_sim()
+    d = dict(kind=kind, **_line_inputs(sim))
+    d["fields"] = np.array([sim.spec.electric_potential.get_electric_field_amplitude(sim.times[n]) for n in range(1, len(sim.times))], dtype=np.float64)
+    d["state_rows"] = np.array([np.asarray(sim.mesh.get_g_for_state(s), dtype=np.complex128) for s in sim.spec.test_states])
+    d["initial_state_index"] = sim.spec.test_states.index(sim.spec.initial_state)
+    # the initial g of a real state is float64, and SumOfOperators.apply accumulates complex terms into zeros_like(g)
+    # (mesh_operators.py:127-131): same values, complex dtype, so that the reference can evaluate its expectation values at t_0
+    sim.mesh.g = sim.mesh.g.astype(np.complex128)
+    # LineLengthGaugeOperators.z returns a bare tuple (mesh_operators.py:347-349), which QuantumMesh.expectation_value cannot
+    # apply (meshes.py:212), so ZExpectationValue cannot be attached on a line mesh; the reference's own operator is wrapped in
+    # its SumOfOperators and evaluated with its own expectation_value at the data times
+    from ionization.mesh import mesh_operators as _mo
+
+    zs = []
+    sim.run(callback=lambda s_: zs.append(s_.mesh.expectation_value(None, _mo.SumOfOperators(*s_.spec.operators.z(s_.mesh)))))
+    d.update(_outputs(sim))
+    d["internal_energy"] = sim.data.internal_energy_expectation_value.copy()
+    d["z_expectation"] = np.array(zs)[sim.data_mask]
+    d.update({f"const_{k}": v for k, v in CONSTANTS.items()})
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **d)
+    print(f"{name}: {kind} line datastores ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
+    return d
+
+
 # --------------------------------------------------------------------------
 # the cases
 # --------------------------------------------------------------------------
@@ -315,6 +406,9 @@ def cases(big):
         "sh_vel_so_datastores_120x12", "sh_vel_so", small_sh_kwargs(120, 12, 50, 20), extra_datastores=True
     )
 
+    # analysis at snapshot / data times
+    yield "sh_len_so_analysis_90x8", lambda: dump_sh_analysis("sh_len_so_analysis_90x8", small_sh_kwargs(90, 8, 60, 20))
+
     # --- config 1: SH r_bound=100 a0, 500x50, Sinc 200 as + logistic window, 2000 steps
     def c1(kind):
         pw = 200 * u.asec
@@ -362,6 +456,10 @@ def cases(big):
         for Z in (1024, 1023):
             n = f"{kind}_{Z}"
             yield n, lambda n=n, kind=kind, Z=Z: dump_line(n, kind, line_kwargs(Z, 50))
+
+    for kind in ("line_len_cn", "line_len_so"):
+        n = f"{kind}_datastores_512"
+        yield n, lambda n=n, kind=kind: dump_line_datastores(n, kind, line_kwargs(512, 40))
 
     if not big:
         return

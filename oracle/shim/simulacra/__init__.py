@@ -170,6 +170,10 @@ if not hasattr(_integ, "cumtrapz"):
     _integ.cumtrapz = _integ.cumulative_trapezoid
 if not hasattr(_integ, "trapz"):
     _integ.trapz = _integ.trapezoid
+import scipy.special as _special  # noqa: E402
+
+if not hasattr(_special, "sph_harm"):  # removed upstream; old signature sph_harm(m, n, azimuth, polar) (reference: meshes.py:1173, :1483)
+    _special.sph_harm = lambda m, n, theta, phi: _special.sph_harm_y(n, m, phi, theta)
 if not hasattr(scipy, "interp"):
     scipy.interp = _interp
 
