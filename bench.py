@@ -316,8 +316,8 @@ def extra_c4_scan(rank, world, local_rank, stream, n_t=200, n_fluence=64, n_phas
     ph = np.linspace(0, u.twopi, n_phase, endpoint=False)
     start = 1000 - n_t // 2
     times = p["times"][start : start + n_t + 1]
-    cols = [C.field_series("sh_len_so", configs.sinc_pulse(200 * u.asec, flu[m // n_phase], ph[m % n_phase]), times, p["time_step"]) for m in range(b0, b1)]
-    fields = np.ascontiguousarray(np.array(cols).T)
+    pulses = [configs.sinc_pulse(200 * u.asec, flu[m // n_phase], ph[m % n_phase]) for m in range(b0, b1)]
+    fields = C.field_series_batch("sh_len_so", pulses, times, p["time_step"], device=local_rank)  # E(t + dt/2) of the rank's members: one kernel (csrc/fields.cuh)
     taus = np.ascontiguousarray(p["taus"][start : start + n_t])
     what = nat.OBS_NORM | nat.OBS_INNER_PRODUCTS
     mask = np.zeros(n_t, dtype=np.uint8)

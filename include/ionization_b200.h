@@ -198,6 +198,19 @@ int ion_sim_halo_status(ion_sim_t *sim, int64_t *exchanges_done, int *aborted);
 /* raw device pointer of the wavefunction in internal layout + its size (for peer copies / checksums) */
 int ion_sim_device_psi(ion_sim_t *sim, void **device_ptr, int64_t *n_bytes);
 
+/* ---- field set-up on the device -------------------------------
+ * The per-step field scalars of a whole scan of windowed Sinc pulses (potentials/pulses.py:599-1013, windows.py:129-168) in the
+ * layout ion_sim_step takes: out float64 [n_times - 1][n_pulses].
+ *   kind ION_FIELD_E: out[n-1][b] = E_b(times[n] + t_offset)                                   (length gauge: mesh_operators.py:1011-1013, :321-323)
+ *   kind ION_FIELD_A: out[n-1][b] = -simps(E_b(times[0..n]), times[0..n]), old-scipy even='avg' (velocity gauge: :1184-1186, pulses.py:58-77),
+ *                     every prefix in one O(n) sweep per pulse instead of the reference's O(n^2).
+ * pulse_params float64 [n_pulses][8]: amplitude, delta_omega, omega_carrier, phase, pulse_center, window_time, window_width
+ * (<= 0: no window), window_center. */
+#define ION_FIELD_E 0
+#define ION_FIELD_A 1
+int ion_sinc_pulse_fields(int device, int kind, int64_t n_times, const double *times, double t_offset, int64_t n_pulses,
+                          const double *pulse_params, double *out);
+
 /* ---- measurement ------------------------------------------------------------- */
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int64_t ion_sim_launch_count(ion_sim_t *sim);

@@ -83,6 +83,7 @@ SIGNATURES = {
     "ion_kernel_name": (ctypes.c_char_p, [_i32]),
     "ion_sim_profile": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "ion_fp64_peak": (_i32, [_i32, _f64p]),
+    "ion_sinc_pulse_fields": (_i32, [_i32, _i32, _i64, _vp, _f64, _i64, _vp, _vp]),
 }
 
 

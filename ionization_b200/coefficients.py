@@ -186,3 +186,48 @@ def field_series(program: str, electric_potential, times, time_step):
     if program in ("sh_vel_so", "line_vel_so"):
         return vector_potential_series(electric_potential, times)
     raise ValueError(program)
+
+
+def sinc_pulse_table(pulses):
+    """[n, 8] parameter table of plain windowed Sinc pulses for the device field set-up (include/ionization_b200.h:
+    ion_sinc_pulse_fields), or None if any pulse is something else (a sum, a DC-corrected pulse, another window ...)"""
+    from . import potentials
+
+    rows = []
+    for p in pulses:
+        if type(p) is not potentials.SincPulse:
+            return None
+        w = p.window
+        if type(w) is potentials.LogisticWindow:
+            win = (w.window_time, w.window_width, w.window_center)
+        elif type(w) is potentials.NoTimeWindow:
+            win = (0.0, 0.0, 0.0)
+        else:
+            return None
+        rows.append((p.amplitude, p.delta_omega, p.omega_carrier, p.phase, p.pulse_center) + win)
+    return np.ascontiguousarray(rows, dtype=np.float64)
+
+
+def field_series_batch(program: str, pulses, times, time_step, device=None):
+    """``field_series`` for every pulse of a scan -> [n_steps, n_pulses].  Plain windowed Sinc pulses are evaluated on the GPU
+    (two kernels for the whole scan, csrc/fields.cuh) when ``device`` is given; anything else, pulse by pulse on the host."""
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    table = sinc_pulse_table(pulses) if device is not None else None
+    if table is None or len(times) < 2:
+        return np.ascontiguousarray(np.array([field_series(program, p, times, time_step) for p in pulses]).T)
+    import ctypes
+
+    from . import _native as nat
+
+    if program in ("sh_len_so", "sh_len_adi"):
+        kind, offset = 0, float(time_step) / 2
+    elif program in ("line_len_cn", "line_len_so"):
+        kind, offset = 0, 0.0
+    elif program in ("sh_vel_so", "line_vel_so"):
+        kind, offset = 1, 0.0
+    else:
+        raise ValueError(program)
+    out = np.empty((len(times) - 1, len(table)), dtype=np.float64)
+    nat.check(nat.load().ion_sinc_pulse_fields(int(device), kind, len(times), nat.ptr(times), ctypes.c_double(offset), len(table), nat.ptr(table), nat.ptr(out)),
+              "ion_sinc_pulse_fields")
+    return out

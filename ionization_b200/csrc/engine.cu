@@ -28,6 +28,7 @@
 #include "adi.cuh"
 #include "ensemble.cuh"
 #include "halo.cuh"
+#include "fields.cuh"
 
 namespace {
 
@@ -1920,6 +1921,42 @@ int ion_sim_device_psi(ion_sim_t *s, void **device_ptr, int64_t *n_bytes)
     *device_ptr = s->psi;
     *n_bytes = (int64_t)((size_t)s->batch * s->L * s->Rp * sizeof(cplx));
     return ION_OK;
+}
+
+int ion_sinc_pulse_fields(int device, int kind, int64_t n_times, const double *times, double t_offset, int64_t n_pulses, const double *pulse_params,
+                          double *out)
+{
+    if (!times || !pulse_params || !out) return fail(ION_EINVAL, "NULL argument");
+    if (n_times < 2 || n_pulses < 1) return fail(ION_EINVAL, "need n_times >= 2 and n_pulses >= 1");
+    if (kind != ION_FIELD_E && kind != ION_FIELD_A) return fail(ION_EINVAL, "kind must be ION_FIELD_E or ION_FIELD_A");
+    if (ion_device_count() <= device || device < 0) return fail(ION_ENODEVICE, "no CUDA device " + std::to_string(device));
+    CUDA_TRY(cudaSetDevice(device));
+    double *d_t = nullptr, *d_e = nullptr, *d_out = nullptr;
+    ion::SincPulseParams *d_p = nullptr;
+    auto cleanup = [&]() { cudaFree(d_t), cudaFree(d_e), cudaFree(d_out), cudaFree(d_p); };
+    const size_t n_e = (size_t)n_times * n_pulses, n_out = (size_t)(n_times - 1) * n_pulses;
+    int rc = ION_OK;
+    do {
+        if ((rc = dev_alloc(&d_t, (size_t)n_times)) || (rc = dev_alloc(&d_e, n_e)) || (rc = dev_alloc(&d_p, (size_t)n_pulses)) ||
+            (kind == ION_FIELD_A && (rc = dev_alloc(&d_out, n_out))))
+            break;
+        cudaError_t e = cudaMemcpy(d_t, times, (size_t)n_times * sizeof(double), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_p, pulse_params, (size_t)n_pulses * sizeof(ion::SincPulseParams), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            // E: the samples the step n -> n + 1 uses are times[1..] + offset; A: samples at times[0..] (offset 0), then every prefix
+            ion::k_sinc_field<<<dim3((unsigned)((n_pulses + 127) / 128), (unsigned)n_times), 128>>>(d_t, kind == ION_FIELD_E ? t_offset : 0.0, (int)n_times, d_p, (int)n_pulses, d_e);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess && kind == ION_FIELD_A) {
+            ion::k_prefix_simps<<<(unsigned)((n_pulses + 127) / 128), 128>>>(d_e, d_t, (int)n_times, (int)n_pulses, -1.0, d_out);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess)
+            e = cudaMemcpy(out, kind == ION_FIELD_A ? d_out : d_e + n_pulses, n_out * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(ION_ECUDA, std::string("ion_sinc_pulse_fields: ") + cudaGetErrorString(e));
+    } while (0);
+    cleanup();
+    return rc;
 }
 
 int64_t ion_sim_launch_count(ion_sim_t *s) { return s ? s->launch_count : 0; }

@@ -69,6 +69,17 @@ class MeshEnsemble:
         for spec in specs[1:]:
             self.sims.append(self._clone_member(first, spec))
         self.batch = len(self.sims)
+        # the per-step field scalars of all members: two kernels for the whole scan when the pulses are plain windowed Sinc
+        # pulses (csrc/fields.cuh), else pulse by pulse on the host -- as each member's own to_sim() would
+        from .. import coefficients as C
+
+        pulses = [s.spec.electric_potential for s in self.sims]
+        try:
+            fields = C.field_series_batch(first._program, pulses, first.times, first.spec.time_step, device=device)
+        except exceptions.NoCudaDevice:
+            fields = C.field_series_batch(first._program, pulses, first.times, first.spec.time_step, device=None)
+        for i, s in enumerate(self.sims):
+            s._fields = np.ascontiguousarray(fields[:, i])
 
     @staticmethod
     def _clone_member(first, spec):
@@ -92,7 +103,7 @@ class MeshEnsemble:
         spec.initial_state = first.spec.initial_state
         spec.device = first.device
         sim.spec = spec
-        sim._fields = C.field_series(first._program, spec.electric_potential, first.times, spec.time_step)
+        sim._fields = None  # filled for all members at once (MeshEnsemble.__init__)
         sim._host_field_cache = None
         sim.mesh = copy.copy(first.mesh)
         sim.mesh.sim = sim

@@ -136,3 +136,25 @@ def test_one_simulation_l_block_sharded_behind_the_mesh_api(gauge):
         assert np.max(np.abs(sim.data.norm_by_l[sh] - ref.data.norm_by_l[sh])) < 1e-12
     with pytest.raises(ion.exceptions.UnsupportedConfiguration):
         spec(devices=[0, 0], datastores=[D.Norm(), D.ZExpectationValue()]).to_sim().run()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("program", ["sh_len_so", "line_len_cn", "sh_vel_so"])
+def test_device_field_setup_equals_the_host_path(program):
+    """E(t) / A(t) of a whole scan of windowed Sinc pulses in two kernels (csrc/fields.cuh) against the host builders,
+    which are checked against the reference's own per-step values (tests/test_host_layer.py)"""
+    from ionization_b200 import coefficients as C
+
+    pw = 200 * u.asec
+    times = C.time_grid(-5 * pw, 5 * pw, 1 * u.asec)
+    pulses = [P.SincPulse(pulse_width=pw, fluence=f * u.Jcm2, phase=ph, window=P.LogisticWindow(window_time=4 * pw, window_width=0.2 * pw))
+              for f in np.geomspace(0.01, 20, 7) for ph in np.linspace(0, u.twopi, 5, endpoint=False)]
+    pulses.append(P.SincPulse(pulse_width=93 * u.asec, fluence=2 * u.Jcm2, phase=1.0, pulse_center=50 * u.asec))  # no window, off-centre
+    host = C.field_series_batch(program, pulses, times, 1 * u.asec, device=None)
+    dev = C.field_series_batch(program, pulses, times, 1 * u.asec, device=0)
+    assert dev.shape == host.shape == (len(times) - 1, len(pulses))
+    scale = np.max(np.abs(host), axis=0)
+    assert np.max(np.abs(dev - host) / scale[None, :]) < 1e-12
+    # anything that is not a plain windowed Sinc pulse goes pulse by pulse on the host (here: a DC-corrected pulse is a sum)
+    corrected = P.DC_correct_electric_potential(pulses[0], times)
+    assert C.sinc_pulse_table([corrected]) is None
