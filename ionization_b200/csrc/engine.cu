@@ -636,10 +636,10 @@ int len_fold_prepare(ion_sim *s)
 int launch_len_ens(ion_sim *s, const ion::UnitParams &p)
 {
     const int n_pairs = s->L / 2 - 1;
-    const long long n_tasks = (long long)s->batch * n_pairs;
+    const long long n_items = (long long)n_pairs * ((s->batch + ion::ENS_MB - 1) / ion::ENS_MB);
     cudaLaunchConfig_t cfg;
     std::memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)std::min<long long>(n_tasks, s->ens_ctas));
+    cfg.gridDim = dim3((unsigned)std::min<long long>(n_items, s->ens_ctas));
     cfg.blockDim = dim3(s->T);
     cfg.dynamicSmemBytes = ion::ens_smem_bytes(s->T);
     cfg.stream = s->stream;
@@ -649,7 +649,7 @@ int launch_len_ens(ion_sim *s, const ion::UnitParams &p)
     cfg.attrs = attr;
     cfg.numAttrs = s->use_pdl ? 1 : 0;
     prof_begin(s, KK_LEN_ENS);
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_len_ens, p, n_pairs, n_tasks));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_len_ens, p, n_pairs, s->batch));
     prof_end(s);
     s->launch_count++;
     ion::UnitParams q = p;  // l = 0 and l = L - 1: units 0 and L/2 of the odd sweep
