@@ -561,6 +561,17 @@ int ensure_factor(ion_sim *s, double tau)
                 return fail(ION_ENOTSUP,
                             "LineMesh Crank-Nicolson rebuilds its pivots per warp and needs the LU multipliers to decay below 1e-30 "
                             "over 256 rows; this time step is too large for the mesh spacing");
+            {   // the bound above is field-free; with the field the diagonal carries tau E w_z as well, and where that cancels the kinetic
+                // diagonal the multipliers decay slowest: |lambda| = (sqrt(1 + 4 a^2) - 1) / (2 a), a = tau |h_off|.  The truncations of this
+                // program (128-row pivot memory, 256-row inflow / segment halos) must stay below double precision for ANY field.
+                double a = 0.0;
+                for (double v : s->h_off_host) a = std::max(a, std::fabs(tau * v));
+                const double lam = a > 0.0 ? (std::sqrt(1.0 + 4.0 * a * a) - 1.0) / (2.0 * a) : 0.0;
+                if (nw > 1 && (std::pow(lam, 256.0) > 1e-16 || std::pow(lam * lam, 128.0) > 1e-16))
+                    return fail(ION_ENOTSUP,
+                                "LineMesh Crank-Nicolson: tau * h_off = " + std::to_string(a) + " is too large for the truncated scans of this program to "
+                                "stay exact when the field's potential cancels the kinetic diagonal (reduce time_step or increase the spacing)");
+            }
             if (int rc = dev_alloc(&s->th, (size_t)s->Rp)) return rc;
             ion::k_make_th<<<(s->Rp + 127) / 128, 128, 0, s->stream>>>(s->h_diag, tau, s->R, s->M, s->T, s->th);
             CUDA_TRY(cudaGetLastError());

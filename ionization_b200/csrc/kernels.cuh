@@ -631,11 +631,12 @@ ION_DEVINL void line_cn_factors(CnFactors<M> &f, const cplx (&D)[M], const doubl
         X = Y;
     }
     mat_normalize(X);
-    // four steps: every lane ends up with the composition over (up to) the 16 threads = 64 rows before it.  That is all a
-    // pivot remembers: it forgets its starting value at the rate |o/p|^2 per row, < 1e-30 over 64 rows under the decay
-    // bound this program requires, so a fifth step (and the exact entry pivot for lanes >= 16) would change nothing.
+    // five steps: every lane ends up with the composition over all the threads of its warp before it (up to 128 rows).  A pivot
+    // forgets its starting value at the rate |o / p|^2 per row.  Field-free that is < 1e-30 over 64 rows under the decay bound this
+    // program requires -- but the diagonal also carries tau E w_z, and where the field's potential cancels the kinetic diagonal
+    // the rate rises to ~0.7 per row (config 2 at 10 J/cm^2: 64 rows left 1e-10, measured against the oracle); 128 rows: 1e-20.
 #pragma unroll
-    for (int s = 1; s < 16; s <<= 1) {
+    for (int s = 1; s < 32; s <<= 1) {
         Mat2 Y = mat_shfl_up(X, s);
         if (lane >= s) {
             X = mat_mul(X, Y);
