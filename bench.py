@@ -284,6 +284,38 @@ def e2e_with_setup(local_rank):
             "api": "ionization_b200.mesh.SphericalHarmonicSpecification(...).to_sim().run(), wall clock, first call in the process (LU factors + graph capture included)"}
 
 
+def extra_observed_every_step(problem, local_rank, stream, n_t=256):
+    """store_data_every = 1 (the reference's default, mesh/sims.py:471): norm, inner products and norm by l after EVERY step.  On the
+    fused schedule the reductions ride inside the step kernels (k_slab<OBS> / k_unit<LEN_STEP_OBS>); the ratio to the unobserved step is the
+    cost of observing (north_star 4)."""
+    import torch
+
+    from ionization_b200 import _native as nat
+    from ionization_b200 import engine
+
+    what = nat.OBS_NORM | nat.OBS_INNER_PRODUCTS | nat.OBS_NORM_BY_L
+    n_t = min(n_t, len(problem["taus"]))
+    start = max(0, len(problem["taus"]) // 2 - n_t // 2)
+    taus, fields = problem["taus"][start : start + n_t], problem["fields"][start : start + n_t]
+    out = {"time_steps": n_t, "observables": "norm, inner products with the test states, norm by l"}
+    with engine.DeviceSimulation.from_problem(problem, device=local_rank) as sim:
+        sim.set_stream(stream.cuda_stream)
+        for name, mask in (("unobserved", np.zeros(n_t, dtype=np.uint8)), ("every_step", np.ones(n_t, dtype=np.uint8))):
+            sim.run(taus, fields, mask, what)  # warm-up: graph capture for this pattern
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            rec = sim.run(taus, fields, mask, what)
+            e1.record(stream)
+            e1.synchronize()
+            out[f"us_per_time_step_{name}"] = 1e3 * e0.elapsed_time(e1) / n_t
+            if name == "every_step":
+                out["records"] = int(rec.shape[0])
+                out["final_norm"] = float(rec[-1, 0, 0])
+    out["ratio"] = out["us_per_time_step_every_step"] / out["us_per_time_step_unobserved"]
+    return out
+
+
 def _all_ok(ok, distributed):
     """collective vote: did every rank get through its (collective-free) set-up?  Keeps the ranks in step when one of them fails."""
     if not distributed:
@@ -702,6 +734,11 @@ def main():
     extra = None
     if args.workload == "c3_vel" and not args.no_extras:
         extra = {}
+        if rank == 0:
+            try:
+                extra["observed_every_step"] = extra_observed_every_step(problem, local_rank, stream)
+            except Exception as exc:  # noqa: BLE001
+                extra["observed_every_step"] = {"error": f"{type(exc).__name__}: {exc}"}
         for name, fn in (("c4_scan", lambda: extra_c4_scan(rank, world, local_rank, stream)), ("c5_sharded", lambda: extra_c5_sharded(rank, world, local_rank))):
             try:
                 extra[name] = fn()

@@ -86,3 +86,62 @@ def test_halo_exchange_world_size_2_and_3_gloo():
             assert lo == (10.0 * (rank - 1) + 2 + 300 if rank > 0 else -1.0)
             assert hi == (10.0 * (rank + 1) + 1 + 300 if rank < world - 1 else -1.0)
             assert rec == [sum(r + 1.0 for r in range(world)), sum(2.0 * r for r in range(world))]
+
+
+class _Spec:
+    def __init__(self, k):
+        self.k = k
+        self.name = f"m{k}"
+
+
+class _Sim:
+    def __init__(self, spec, device):
+        self.spec, self.device, self.mesh = spec, device, None
+
+
+def _fake_block(specs, device=0, keep_mesh=False):
+    return [_Sim(s, device) for s in specs]
+
+
+def _scan_worker(rank, world, port, results):
+    import torch.distributed as dist
+
+    from ionization_b200 import scan
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["LOCAL_RANK"] = str(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        scan.run_block = _fake_block  # the batched device run of a block is GPU work; the sharding and the gather are what is tested here
+        sims = scan.run_scan([_Spec(k) for k in range(7)])
+        results[rank] = [(s.spec.k, s.device) for s in sims]
+    finally:
+        dist.destroy_process_group()
+
+
+def test_scan_is_split_into_contiguous_blocks_and_gathered_on_every_rank_gloo():
+    """ionization_b200.scan.run_scan under a process group (world_size 2 and 3): rank r runs block shard_range(n, r, world) on its
+    LOCAL_RANK device and every rank receives all simulations in the order of the specs (scan_utils.py:638-663 maps run(spec))"""
+    import torch.multiprocessing as mp
+
+    for world in (2, 3):
+        port = _free_port()
+        mgr = mp.Manager()
+        results = mgr.dict()
+        mp.spawn(_scan_worker, args=(world, port, results), nprocs=world, join=True)
+        expect = []
+        for r in range(world):
+            b0, b1 = parallel.shard_range(7, r, world)
+            expect += [(k, r) for k in range(b0, b1)]
+        for rank in range(world):
+            assert results[rank] == expect
+
+
+def test_scan_over_several_devices_of_one_process_keeps_the_order(monkeypatch):
+    from ionization_b200 import scan
+
+    monkeypatch.setattr(scan, "run_block", _fake_block)
+    sims = scan.run_scan([_Spec(k) for k in range(10)], devices=[3, 5, 6])
+    assert [s.spec.k for s in sims] == list(range(10))
+    assert [s.device for s in sims] == [3] * 4 + [5] * 3 + [6] * 3
