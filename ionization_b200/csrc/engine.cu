@@ -111,6 +111,7 @@ struct ion_sim {
     cplx *peer_stage[2] = {nullptr, nullptr};       // the neighbours' staging slots facing this shard (peer mappings)
     void *peer_ipc_base[2] = {nullptr, nullptr};    // IPC mappings to close
     bool peers_attached = false;
+    bool neighbour_on_same_device = false;  // a linked neighbour lives on this GPU (several shards of one process on one device)
     bool use_len_fold = true;
     bool use_ens = true;
     int ens_state = 0;  // scan ensembles: persistent folded length-gauge kernel with a prefetch pipeline (ensemble.cuh); 0 / 1 / -1 as above
@@ -376,7 +377,10 @@ ion::UnitParams base_params(ion_sim *s)
 int launch_len_ens(ion_sim *s, const ion::UnitParams &p);
 int launch_observe_finish(ion_sim *s, uint32_t what, double *dev_out);
 
-int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, const double *sb, uint32_t obs_what = 0)
+// a subset of the units of a launch: units sub_unit0 + k * sub_stride, k < sub_count (sub_count == 0: all units).  do_swap = false:
+// an out-of-place kernel leaves the buffer swap to the launch that covers the remaining units
+int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, const double *sb, uint32_t obs_what = 0, int sub_unit0 = 0, int sub_stride = 1,
+                int sub_count = 0, bool do_swap = true)
 {
     ion::UnitParams p = base_params(s);
     p.parity = parity;
@@ -396,6 +400,11 @@ int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, c
         case ion::PROG_LINE_SO_VEL:
         case ion::PROG_LINE_CN: units = s->L; break;
         default: units = ion::num_units(s->L, s->l_begin, parity);
+    }
+    if (sub_count > 0) {
+        p.unit0 = sub_unit0;
+        p.unit_stride = sub_stride;
+        units = sub_count;
     }
     dim3 grid(units * s->S, s->batch);
     if (prog == ion::PROG_ROT) p.H = 0;  // point-wise in r: interior threads only
@@ -470,7 +479,7 @@ int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, c
     }
     prof_end(s);
     s->launch_count++;
-    if (seg_oop && rc == ION_OK) std::swap(s->psi, s->psi2);
+    if (seg_oop && rc == ION_OK && do_swap) std::swap(s->psi, s->psi2);
     return rc;
 }
 
@@ -859,6 +868,35 @@ int launch_exchange(ion_sim *s)
     return ION_OK;
 }
 
+// An odd-parity kernel of a linked l-block shard.  Only its first and last unit touch a ghost channel, so only they have to wait
+// for the halo exchange: the exchange (NVLink latency + rendezvous with both neighbours) and those two units run on a side
+// branch while the main stream does all the interior units -- the hand-shake is off the critical path as long as the
+// neighbours are less than one interior kernel apart.  Works alike for plain launches and inside a stream capture (the event
+// record / wait pairs become graph edges).  Used when every neighbour lives on another device (one shard per GPU): with several
+// shards on ONE device a spinning exchange kernel at the head of a hardware work queue can hold back another shard's kernels
+// that the driver mapped to the same queue, so those (tests, devices=[0, 0, ..]) keep one stream per shard.
+int launch_odd_exchanged(ion_sim *s, int prog, int flags, const double *sa)
+{
+    const int units = ion::num_units(s->L, s->l_begin, 1);
+    const char *env = std::getenv("ION_SERIAL_EXCHANGE");
+    if (!s->peers_attached || !s->side || units < 3 || s->profiling || (env && env[0] == '1') || s->neighbour_on_same_device) {
+        if (int rc = launch_exchange(s)) return rc;
+        return launch_unit(s, prog, 1, flags, sa, nullptr);
+    }
+    CUDA_TRY(cudaEventRecord(s->ev_fork, s->stream));
+    CUDA_TRY(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
+    cudaStream_t main_stream = s->stream;
+    s->stream = s->side;
+    int rc = launch_exchange(s);
+    if (rc == ION_OK) rc = launch_unit(s, prog, 1, flags, sa, nullptr, 0, 0, units - 1, 2, false);  // units 0 and units - 1
+    s->stream = main_stream;
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(s->ev_done[0], s->side));
+    if ((rc = launch_unit(s, prog, 1, flags, sa, nullptr, 0, 1, 1, units - 2, true))) return rc;                    // units 1 .. units - 2
+    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_done[0], 0));
+    return ION_OK;
+}
+
 // what a step's tail does of the next step's head when the two are fused (no observation in between)
 int fuse_level(const ion_sim *s) { return s->slab_state == 1 ? 2 : 1; }
 
@@ -892,8 +930,7 @@ int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, int pre, b
             }
             if (fast_l_path(s)) {
                 if (pre < 1 && (rc = launch_unit(s, PROG_ROT, 0, 0, sa, nullptr))) return rc;
-                if ((rc = launch_exchange(s))) return rc;
-                if ((rc = launch_unit(s, PROG_ROT_CN_ROT, 1, 0, sa, nullptr))) return rc;
+                if ((rc = launch_odd_exchanged(s, PROG_ROT_CN_ROT, 0, sa))) return rc;
                 return launch_unit(s, PROG_ROT, 0, F_MASK, sa, fuse_next ? sb_next : nullptr);
             }
             if ((rc = launch_sweep_flat(s, 0, 0, sa))) return rc;
@@ -906,19 +943,17 @@ int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, int pre, b
             const bool fast = fast_l_path(s);
             if (fast) {
                 if (pre < 1 && (rc = launch_unit(s, PROG_ROT, 0, F_REAL_ROT, sa, nullptr))) return rc;
-                if (pre < 2 && ((rc = launch_exchange(s)) || (rc = launch_unit(s, PROG_ROT, 1, F_REAL_ROT, sa, nullptr)))) return rc;
+                if (pre < 2 && (rc = launch_odd_exchanged(s, PROG_ROT, F_REAL_ROT, sa))) return rc;
             } else {
                 if ((rc = launch_sweep_flat(s, 0, F_REAL_ROT, sa))) return rc;
                 if ((rc = launch_sweep_flat(s, 1, F_REAL_ROT, sa))) return rc;
             }
             if (pre < 2 && (rc = launch_unit(s, PROG_H2, 0, 0, sa, nullptr))) return rc;   // ee, eo
-            if ((rc = launch_exchange(s))) return rc;
-            if ((rc = launch_unit(s, PROG_H2_CN_H2, 1, 0, sa, nullptr))) return rc;        // oe, oo, CN, oo, oe
+            if ((rc = launch_odd_exchanged(s, PROG_H2_CN_H2, 0, sa))) return rc;           // oe, oo, CN, oo, oe
             if (fast && fuse_next && s->slab_state == 1) return launch_slab(s, sa, sb_next, cur.what, cur.dst);  // eo ee h1_o h1_e mask | h1_e h1_o ee eo
             if ((rc = launch_unit(s, PROG_H2, 0, F_H2_REVERSE, sa, nullptr))) return rc;   // eo, ee
             if (fast) {
-                if ((rc = launch_exchange(s))) return rc;
-                if ((rc = launch_unit(s, PROG_ROT, 1, F_REAL_ROT, sa, nullptr))) return rc;
+                if ((rc = launch_odd_exchanged(s, PROG_ROT, F_REAL_ROT, sa))) return rc;
                 return launch_unit(s, PROG_ROT, 0, F_REAL_ROT | F_MASK, sa, fuse_next ? sb_next : nullptr);
             }
             if ((rc = launch_sweep_flat(s, 1, F_REAL_ROT, sa))) return rc;
@@ -1761,7 +1796,9 @@ int ion_sim_attach_peer(ion_sim_t *s, int side, const void *blob, int64_t blob_b
         // several shards of ONE process on different GPUs (mesh API: SphericalHarmonicSpecification(devices=[...])): the
         // neighbour's halo block is dereferenced by this device's kernels, which needs peer access between the two devices
         cudaPointerAttributes pa;
-        if (cudaPointerGetAttributes(&pa, pblock) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device != s->device) {
+        const cudaError_t pe = cudaPointerGetAttributes(&pa, pblock);
+        if (pe != cudaSuccess || pa.type != cudaMemoryTypeDevice || pa.device == s->device) s->neighbour_on_same_device = true;
+        if (pe == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device != s->device) {
             int can = 0;
             CUDA_TRY(cudaDeviceCanAccessPeer(&can, s->device, pa.device));
             if (!can) return fail(ION_ENOTSUP, "devices " + std::to_string(s->device) + " and " + std::to_string(pa.device) + " cannot access each other's memory (no NVLink / PCIe peer path)");
@@ -1782,6 +1819,11 @@ int ion_sim_attach_peer(ion_sim_t *s, int side, const void *blob, int64_t blob_b
     s->peer_stage[side] = reinterpret_cast<cplx *>(pblock + ion::HF_COUNT) + (size_t)facing * 2 * s->Rp;
     s->peers_attached = (!s->g_lo || s->peer_flags[0]) && (!s->g_hi || s->peer_flags[1]);
     s->invalidate_graphs();
+    if (!s->side) {  // side branch for the exchange and the two boundary units of every odd-parity kernel (launch_odd_exchanged)
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+        for (auto &e : s->ev_done) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     return ION_OK;
 }
 
