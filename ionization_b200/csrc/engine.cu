@@ -275,7 +275,7 @@ size_t unit_smem_bytes(const ion_sim *s, int prog = -1)
 {
     size_t n = (256 + 4 * (size_t)s->Tc) * sizeof(cplx);
     const bool cn_pair = (prog == ion::PROG_ROT_CN_ROT || prog == ion::PROG_H2_CN_H2 || prog == ion::PROG_LEN_STEP || prog == ion::PROG_LEN_STEP_OBS || prog < 0);
-    if (cn_pair && s->M == 4 && s->S == 1 && s->tmax <= 512) n += 8 * (size_t)s->Tc * sizeof(cplx) + 9 * (size_t)(s->Tc / 2) * sizeof(double);
+    if (cn_pair && s->M == 4 && s->tmax <= 512) n += 8 * (size_t)s->Tc * sizeof(cplx) + 9 * (size_t)(s->Tc / 2) * sizeof(double);
     return n;
 }
 
@@ -318,6 +318,7 @@ int set_unit_smem_attr()
     if (PROG == ion::PROG_ROT_CN_ROT || PROG == ion::PROG_H2_CN_H2 || PROG == ion::PROG_LEN_STEP || PROG == ion::PROG_LEN_STEP_OBS) {
         CUDA_TRY(cudaFuncSetAttribute(ion::k_unit<4, PROG, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(ion::k_unit<4, PROG, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(ion::k_unit<4, PROG, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
     }
     return ION_OK;
 }

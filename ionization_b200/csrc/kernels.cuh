@@ -779,7 +779,9 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
     // ---- programs containing Crank-Nicolson ----
     // pairs: both channels are solved together in layout 2 (see above); single channels and r-segments keep layout 1
     constexpr bool LENSTEP = (PROG == PROG_LEN_STEP || PROG == PROG_LEN_STEP_OBS), OBS = (PROG == PROG_LEN_STEP_OBS);
-    constexpr bool L2CN = (M == 4) && !SEG && (TMAX <= 512) && (PROG == PROG_ROT_CN_ROT || PROG == PROG_H2_CN_H2 || LENSTEP);
+    // (r-segments included: the thread's position in the channel is t = segment offset + tl, halo threads beyond either end of the
+    // channel -- !ok -- carry identity factors and zero multipliers, and the recurrences start from zero at the edge of the halo)
+    constexpr bool L2CN = (M == 4) && (TMAX <= 512) && (PROG == PROG_ROT_CN_ROT || PROG == PROG_H2_CN_H2 || LENSTEP);
 #ifdef ION_EXP_CLOCKS  // timing-only instrumentation: phase time stamps of two CTAs (first and second wave)
     long long ck[8];
 #define ION_CK(i) ck[i] = clock64()
@@ -796,23 +798,27 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         // The small coefficient loads go FIRST: the 64 KB of LU factors of a 512-thread CTA keep the SM's load path busy for
         // ~1500 cycles, and everything queued behind them (and the trigonometry that waits for it) would be exposed in every CTA
         // of a second wave, where no previous kernel's tail hides the prologue.
+        const int tp = t - (tl & 1);  // position in the channel of the lane pair's first thread (tp == 2 pp without r-segments)
+        const bool ok0 = SEG ? (tp >= 0 && tp < T) : true, ok1 = SEG ? (tp + 1 >= 0 && tp + 1 < T) : true;
         double tov[9];
         if (!odd) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) tov[k] = p.toff[(k & 3) * T + 2 * pp + (k >> 2)];
-            tov[8] = p.toff_prev[2 * pp];
+            for (int k = 0; k < 8; ++k) tov[k] = ((k >> 2) ? ok1 : ok0) ? p.toff[(k & 3) * T + tp + (k >> 2)] : 0.0;
+            tov[8] = ok0 ? p.toff_prev[tp] : 0.0;
         }
         cplx P8, Q8;  // multipliers of the 8-row chunk = product of the two 4-row ones
         cplx aP0, aP1, aQ0, aQ1;
         {
-            const size_t ch = (size_t)(l0 + (odd ? 1 : 0)) * T + 2 * pp;
-            aP0 = ld_c(p.aggP + ch), aP1 = ld_c(p.aggP + ch + 1), aQ0 = ld_c(p.aggQ + ch), aQ1 = ld_c(p.aggQ + ch + 1);
+            const size_t ch = (size_t)(l0 + (odd ? 1 : 0)) * T + tp;
+            aP0 = ok0 ? ld_c(p.aggP + ch) : c_zero(), aP1 = ok1 ? ld_c(p.aggP + ch + 1) : c_zero();
+            aQ0 = ok0 ? ld_c(p.aggQ + ch) : c_zero(), aQ1 = ok1 ? ld_c(p.aggQ + ch + 1) : c_zero();
         }
-        // LU factor of the row before the chunk (row 8pp - 1: the previous lane pair's last row, possibly another warp's)
-        const cplx wprev = pp > 0 ? ld_c(p.w + (size_t)(l0 + (odd ? 1 : 0)) * chan + 3 * (size_t)T + 2 * pp - 1) : c_zero();
+        // LU factor of the row before the chunk (the previous lane pair's last row, possibly another warp's; at the first thread of a
+        // segment its inflow is zero by construction, so the factor does not matter there)
+        const cplx wprev = (pp > 0 && tp > 0 && tp - 1 < T) ? ld_c(p.w + (size_t)(l0 + (odd ? 1 : 0)) * chan + 3 * (size_t)T + tp - 1) : c_zero();
         double cvec[M], czp = 0.0, kap0, kapA = 0.0, kapB = 0.0;
         if (PROG == PROG_ROT_CN_ROT || LENSTEP) {
-            load_vec<M>(cvec, p.vec, T, t, true);
+            load_vec<M>(cvec, p.vec, T, t, ok);
             kap0 = sa * p.cl[p.l_begin + l0];
             if (LENSTEP) {  // a pair always has both even-pair partners: l0 - 1 and l0 + 2
                 // OBS: the previous step's half (s_b) first, on its own -- the observed state sits between the two halves
@@ -820,17 +826,22 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
                 kapB = (OBS ? sb : sa + sb) * p.cl[p.l_begin + l0 + 1];
             }
         } else {
-            load_vec<M>(cvec, p.zvec, T, t, true);
-            czp = p.zprev[t];
+            load_vec<M>(cvec, p.zvec, T, t, ok);
+            czp = ok ? p.zprev[t] : 0.0;
             kap0 = sa * p.cl2[p.l_begin + l0];
         }
         {   // coalesced reads of both channels' factors, permuted on the way into shared memory
-            const cplx *w0 = p.w + (size_t)l0 * chan + tl;
+            const cplx *w0 = p.w + (size_t)l0 * chan + t;
             cplx *dst = wsm + (size_t)(4 * (tl & 1)) * Tc + (tl & ~1);
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
-                cp_async16(dst + (size_t)k4 * Tc, w0 + (size_t)k4 * T);
-                cp_async16(dst + (size_t)k4 * Tc + 1, w0 + chan + (size_t)k4 * T);
+                if (ok) {
+                    cp_async16(dst + (size_t)k4 * Tc, w0 + (size_t)k4 * T);
+                    cp_async16(dst + (size_t)k4 * Tc + 1, w0 + chan + (size_t)k4 * T);
+                } else {  // beyond the channel: identity factors (read by this thread and its lane-pair partner only, after the __syncwarp below)
+                    dst[(size_t)k4 * Tc] = c_make(1.0, 0.0);
+                    dst[(size_t)k4 * Tc + 1] = c_make(1.0, 0.0);
+                }
             }
             cp_async_commit();
         }
@@ -858,8 +869,8 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         ION_CK(1);
         pdl_wait();
         ION_CK(2);
-        load_rows<M>(A, base, T, t, true);
-        load_rows<M>(B, base + chan, T, t, true);
+        load_rows<M>(A, base, T, t, ok);
+        load_rows<M>(B, base + chan, T, t, ok);
 #ifndef ION_H2_TRIG_FIRST
         if (PROG == PROG_H2_CN_H2) pang = rpair_angles<M>(cvec, czp, kap0);
 #endif
@@ -869,30 +880,30 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
             double mk[M];
 #pragma unroll
             for (int k = 0; k < M; ++k) mk[k] = 1.0;
-            if (p.flags & F_MASK) load_vec<M>(mk, p.mask, T, t, true);
+            if (p.flags & F_MASK) load_vec<M>(mk, p.mask, T, t, ok);
             double *osm = reinterpret_cast<double *>(xs);
             cplx Q[M];
-            load_rows<M>(Q, base - chan, T, t, true);
+            load_rows<M>(Q, base - chan, T, t, ok);
             rotate_both<M>(A, Q, eangA);
 #pragma unroll
             for (int k = 0; k < M; ++k) A[k] = c_scale(A[k], mk[k]), Q[k] = c_scale(Q[k], mk[k]);
-            obs_channel<M>(p, A, l0, b, t, true, tl, Tc, osm);
+            obs_channel<M>(p, A, l0, b, t, mine, tl, Tc, osm);
             rotate_member<M>(A, Q, rot_angles_auto<M>(cvec, p.vec_dv, sa * p.cl[p.l_begin + l0 - 1]));
-            load_rows<M>(Q, base + 2 * chan, T, t, true);
+            load_rows<M>(Q, base + 2 * chan, T, t, ok);
             rotate_both<M>(B, Q, eangB);
 #pragma unroll
             for (int k = 0; k < M; ++k) B[k] = c_scale(B[k], mk[k]), Q[k] = c_scale(Q[k], mk[k]);
-            obs_channel<M>(p, B, l0 + 1, b, t, true, tl, Tc, osm);
+            obs_channel<M>(p, B, l0 + 1, b, t, mine, tl, Tc, osm);
             rotate_member<M>(B, Q, rot_angles_auto<M>(cvec, p.vec_dv, sa * p.cl[p.l_begin + l0 + 1]));
         } else if (LENSTEP) {
             cplx Q[M];
-            load_rows<M>(Q, base - chan, T, t, true);
+            load_rows<M>(Q, base - chan, T, t, ok);
             rotate_member<M>(A, Q, eangA);
-            load_rows<M>(Q, base + 2 * chan, T, t, true);
+            load_rows<M>(Q, base + 2 * chan, T, t, ok);
             rotate_member<M>(B, Q, eangB);
             if (p.flags & F_MASK) {
                 double mk[M];
-                load_vec<M>(mk, p.mask, T, t, true);
+                load_vec<M>(mk, p.mask, T, t, ok);
 #pragma unroll
                 for (int k = 0; k < M; ++k) {
                     A[k] = c_scale(A[k], mk[k]);
@@ -916,8 +927,8 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         if (PROG == PROG_ROT_CN_ROT || LENSTEP) rotate_pair<M, false>(A, B, rang);
         else h2_pair<M>(A, B, pang, true, tl, Tc, xs);  // (oo, oe)
         ION_CK(6);
-        store_rows<M>(A, obase, T, t, true);
-        store_rows<M>(B, obase + chan, T, t, true);
+        store_rows<M>(A, obase, T, t, mine);
+        store_rows<M>(B, obase + chan, T, t, mine);
         ION_CK(7);
 #ifdef ION_EXP_CLOCKS
         if ((tl == 0 || tl == 288) && (blockIdx.x == 3 || blockIdx.x == 200) && blockIdx.y == 0)

@@ -1,0 +1,18 @@
+#!/bin/bash
+python -m pytest tests -m gpu -x -q -k "segment or config5 or shard or peer" 2>&1 | tail -4
+python - <<'PY'
+import time, numpy as np, torch
+from ionization_b200 import configs, engine, units as u
+for gauge, R, L, n in (("LEN", 16384, 4096, 40), ("VEL", 8192, 512, 40), ("LEN", 8192, 512, 40)):
+    p = configs.spherical_harmonic_problem(r_bound=0.1 * R * u.bohr_radius, r_points=R, l_bound=L, gauge=gauge, n_steps=n,
+                                           pulse=configs.sinc_pulse(20 * u.asec, 20 * u.Jcm2), time_initial=-n / 2 * u.asec, time_final=n / 2 * u.asec)
+    for env in ({}, {"ION_NO_LEN_FOLD": "1", "ION_NO_SLAB": "1"}):
+        import os
+        for k in ("ION_NO_LEN_FOLD", "ION_NO_SLAB"): os.environ.pop(k, None)
+        os.environ.update(env)
+        with engine.DeviceSimulation.from_problem(p) as sim:
+            st = torch.cuda.Stream(); sim.set_stream(st.cuda_stream)
+            sim.step(p["taus"], p["fields"]); sim.synchronize()
+            t0 = time.perf_counter(); sim.step(p["taus"], p["fields"]); sim.synchronize()
+            print(gauge, R, L, env, f"{1e6 * (time.perf_counter() - t0) / n:.1f} us/step", flush=True)
+PY
