@@ -460,6 +460,7 @@ def extra_c5_sharded(rank, world, local_rank, n_t=100):
     dist.barrier()
     torch.cuda.synchronize()
     l0 = shard.engine.launch_count
+    n_ex0, _ = shard.engine.halo_status()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(shard.stream)
     shard.step_device(p["taus"], p["fields"])
@@ -472,13 +473,14 @@ def extra_c5_sharded(rank, world, local_rank, n_t=100):
     blocks = parallel.gather_objects((shard.l_begin, shard.read_g()))
     shard.close()
     out.update({"ms_per_step": ms, "updates_per_s": R * L / (ms * 1e-3), "hbm_roofline_frac_per_gpu": R * L / (ms * 1e-3) / world * BYTES_PER_UPDATE / (peak * 1e9),
-                "partitioning": f"{world} contiguous l-blocks of {L // world} channels cut at even channels, one ghost channel per neighbour",
-                "halo_bytes_per_exchange_per_neighbour": R * 16, "exchanges_per_step": len(shard.halo_phases), "exchanges_done": n_ex, "halo_aborted": bool(aborted),
+                "partitioning": f"{world} contiguous l-blocks of ~{L // world} channels cut at odd channels (every odd pair local), one ghost channel per neighbour = the read-only "
+                                "even-pair partner of the block's first / last pair; every shard runs the one-kernel folded step (PROG_LEN_STEP) of the unsharded engine",
+                "halo_bytes_per_exchange_per_neighbour": R * 16, "exchanges_per_step": (n_ex - n_ex0) / n_t, "exchanges_done": n_ex, "halo_aborted": bool(aborted),
                 "transport": "engine kernel over NVLink peer memory (CUDA IPC), inside the captured step loop; NCCL only for rendezvous and the scalar all-reduce",
                 "norm": float(rec[0]), "gpu_launches_per_rank": int(launches)})
     if rank == 0:
-        ms_same, g_ref = unsharded({"ION_NO_LEN_FOLD": "1"})
-        ms_best, _ = unsharded({})
+        ms_same, g_ref = unsharded({})  # the shards run the same folded one-kernel step as the unsharded engine
+        ms_best = ms_same
         g = np.concatenate([blk for _, blk in sorted(blocks, key=lambda x: x[0])], axis=0)
         out.update({"max_rel_err_vs_unsharded": float(np.max(np.abs(g - g_ref)) / np.max(np.abs(g_ref))),
                     "unsharded_1gpu_ms_per_step_same_kernels": ms_same, "unsharded_1gpu_ms_per_step_best": ms_best,

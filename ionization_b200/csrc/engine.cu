@@ -92,6 +92,10 @@ struct ion_sim {
     // l-block shard (g_lo, g_hi); L_own / l_own are the owned range.  Unsharded: L == L_own == L_total.
     int L = 0, R = 0, batch = 0, device = 0, L_total = 0, l_begin = 0;
     int L_own = 0, l_own = 0, g_lo = 0, g_hi = 0;
+    // parity of the channels an l-block shard is cut at.  0: blocks begin on even channels -- odd-parity pairs straddle the cuts
+    // (every program).  1: blocks begin on odd channels (length gauge) -- every odd-parity pair is local, so the folded one-pass step
+    // (PROG_LEN_STEP) runs on shards too: its read-only even-pair partners are the ghost channels.
+    int cut_parity = 0;
     // T = threads per channel (row stride of the layout); a channel is cut into S r-segments of T_seg interior threads,
     // each CTA running Tc = T_seg + 2H threads (S == 1: Tc == T_seg == T, H == 0)
     int M = 4, T = 0, Rp = 0, tmax = 0, S = 1, T_seg = 0, H = 0, Tc = 0;
@@ -467,7 +471,7 @@ int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, c
                 prof_begin(s, kind);
                 rc = launch_unit_prog<ion::PROG_LEN_STEP>(s, p, grid);
             }
-            std::swap(s->psi, s->psi2);
+            if (do_swap) std::swap(s->psi, s->psi2);
             break;
         case ion::PROG_LEN_STEP_OBS:  // never the persistent ensemble kernel: the observed step runs one CTA per (unit, member)
             kind = KK_LEN_STEP;
@@ -633,7 +637,9 @@ int len_fold_prepare(ion_sim *s)
     if (s->len_fold_state != 0) return ION_OK;
     s->len_fold_state = -1;
     if (!s->use_len_fold || s->program != ION_SH_LEN_SO || !fast_l_path(s)) return ION_OK;
-    if (s->L_own != s->L_total || s->L < 2) return ION_OK;
+    if (s->L < 2) return ION_OK;
+    // l-block shards: cut at odd channels and linked by the engine's own exchange (the phase API stays on the single-sweep kernels)
+    if (s->L_own != s->L_total && !(s->cut_parity == 1 && s->peers_attached)) return ION_OK;
     if (int rc = ensure_second_buffer(s)) return rc;
     s->len_fold_state = 1;
     // ensembles: persistent CTAs with a prefetch pipeline instead of one short-lived CTA per (pair, member)
@@ -869,31 +875,37 @@ int launch_exchange(ion_sim *s)
     return ION_OK;
 }
 
-// An odd-parity kernel of a linked l-block shard.  Only its first and last unit touch a ghost channel, so only they have to wait
-// for the halo exchange: the exchange (NVLink latency + rendezvous with both neighbours) and those two units run on a side
-// branch while the main stream does all the interior units -- the hand-shake is off the critical path as long as the
-// neighbours are less than one interior kernel apart.  Works alike for plain launches and inside a stream capture (the event
-// record / wait pairs become graph edges).  Used when every neighbour lives on another device (one shard per GPU): with several
-// shards on ONE device a spinning exchange kernel at the head of a hardware work queue can hold back another shard's kernels
-// that the driver mapped to the same queue, so those (tests, devices=[0, 0, ..]) keep one stream per shard.
-int launch_odd_exchanged(ion_sim *s, int prog, int flags, const double *sa)
+// A kernel of a linked l-block shard whose pairs straddle the cuts (parity != cut_parity), or the folded length-gauge step of a
+// shard cut at odd channels (its first and last pair read a ghost channel as their even-pair partner).  Only the first and the
+// last unit touch a ghost channel, so only they have to wait for the halo exchange: the exchange (NVLink latency + rendezvous with
+// both neighbours) and those two units run on a side branch while the main stream does all the interior units -- the hand-shake
+// is off the critical path as long as the neighbours are less than one interior kernel apart.  Works alike for plain launches and
+// inside a stream capture (the event record / wait pairs become graph edges).  Used when every neighbour lives on another device
+// (one shard per GPU): with several shards on ONE device a spinning exchange kernel at the head of a hardware work queue can hold
+// back another shard's kernels that the driver mapped to the same queue, so those (tests, devices=[0, 0, ..]) keep one stream per shard.
+int launch_exchanged(ion_sim *s, int prog, int parity, int flags, const double *sa, const double *sb)
 {
-    const int units = ion::num_units(s->L, s->l_begin, 1);
+    const bool folded = (prog == ion::PROG_LEN_STEP);
+    if (!s->peers_attached || (!folded && parity == s->cut_parity)) return launch_unit(s, prog, parity, flags, sa, sb);
+    // units of the launch: the folded step skips the ghost channels (single-channel units at either end; they belong to the neighbours)
+    const int units_all = ion::num_units(s->L, s->l_begin, parity);
+    const int u0 = folded ? s->g_lo : 0, u1 = units_all - 1 - (folded ? s->g_hi : 0);
+    const int units = u1 - u0 + 1;
     const char *env = std::getenv("ION_SERIAL_EXCHANGE");
-    if (!s->peers_attached || !s->side || units < 3 || s->profiling || (env && env[0] == '1') || s->neighbour_on_same_device) {
+    if (!s->side || units < 3 || s->profiling || (env && env[0] == '1') || s->neighbour_on_same_device) {
         if (int rc = launch_exchange(s)) return rc;
-        return launch_unit(s, prog, 1, flags, sa, nullptr);
+        return launch_unit(s, prog, parity, flags, sa, sb, 0, u0, 1, units, true);
     }
     CUDA_TRY(cudaEventRecord(s->ev_fork, s->stream));
     CUDA_TRY(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
     cudaStream_t main_stream = s->stream;
     s->stream = s->side;
     int rc = launch_exchange(s);
-    if (rc == ION_OK) rc = launch_unit(s, prog, 1, flags, sa, nullptr, 0, 0, units - 1, 2, false);  // units 0 and units - 1
+    if (rc == ION_OK) rc = launch_unit(s, prog, parity, flags, sa, sb, 0, u0, units - 1, 2, false);  // units u0 and u1
     s->stream = main_stream;
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(s->ev_done[0], s->side));
-    if ((rc = launch_unit(s, prog, 1, flags, sa, nullptr, 0, 1, 1, units - 2, true))) return rc;                    // units 1 .. units - 2
+    if ((rc = launch_unit(s, prog, parity, flags, sa, sb, 0, u0 + 1, 1, units - 2, true))) return rc;               // the interior units
     CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_done[0], 0));
     return ION_OK;
 }
@@ -926,13 +938,13 @@ int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, int pre, b
                     rc = launch_observe_finish(s, prev.what, prev.dst);
                     prof_end(s);
                     if (rc) return rc;
-                } else if ((rc = launch_unit(s, PROG_LEN_STEP, 1, pre ? F_MASK : 0, sa, pre ? sa - s->batch : nullptr))) return rc;
-                return fuse_next ? ION_OK : launch_unit(s, PROG_ROT, 0, F_MASK, sa, nullptr);
+                } else if ((rc = launch_exchanged(s, PROG_LEN_STEP, 1, pre ? F_MASK : 0, sa, pre ? sa - s->batch : nullptr))) return rc;
+                return fuse_next ? ION_OK : launch_exchanged(s, PROG_ROT, 0, F_MASK, sa, nullptr);
             }
             if (fast_l_path(s)) {
-                if (pre < 1 && (rc = launch_unit(s, PROG_ROT, 0, 0, sa, nullptr))) return rc;
-                if ((rc = launch_odd_exchanged(s, PROG_ROT_CN_ROT, 0, sa))) return rc;
-                return launch_unit(s, PROG_ROT, 0, F_MASK, sa, fuse_next ? sb_next : nullptr);
+                if (pre < 1 && (rc = launch_exchanged(s, PROG_ROT, 0, 0, sa, nullptr))) return rc;
+                if ((rc = launch_exchanged(s, PROG_ROT_CN_ROT, 1, 0, sa, nullptr))) return rc;
+                return launch_exchanged(s, PROG_ROT, 0, F_MASK, sa, fuse_next ? sb_next : nullptr);
             }
             if ((rc = launch_sweep_flat(s, 0, 0, sa))) return rc;
             if ((rc = launch_sweep_flat(s, 1, 0, sa))) return rc;
@@ -944,17 +956,17 @@ int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, int pre, b
             const bool fast = fast_l_path(s);
             if (fast) {
                 if (pre < 1 && (rc = launch_unit(s, PROG_ROT, 0, F_REAL_ROT, sa, nullptr))) return rc;
-                if (pre < 2 && (rc = launch_odd_exchanged(s, PROG_ROT, F_REAL_ROT, sa))) return rc;
+                if (pre < 2 && (rc = launch_exchanged(s, PROG_ROT, 1, F_REAL_ROT, sa, nullptr))) return rc;
             } else {
                 if ((rc = launch_sweep_flat(s, 0, F_REAL_ROT, sa))) return rc;
                 if ((rc = launch_sweep_flat(s, 1, F_REAL_ROT, sa))) return rc;
             }
             if (pre < 2 && (rc = launch_unit(s, PROG_H2, 0, 0, sa, nullptr))) return rc;   // ee, eo
-            if ((rc = launch_odd_exchanged(s, PROG_H2_CN_H2, 0, sa))) return rc;           // oe, oo, CN, oo, oe
+            if ((rc = launch_exchanged(s, PROG_H2_CN_H2, 1, 0, sa, nullptr))) return rc;     // oe, oo, CN, oo, oe
             if (fast && fuse_next && s->slab_state == 1) return launch_slab(s, sa, sb_next, cur.what, cur.dst);  // eo ee h1_o h1_e mask | h1_e h1_o ee eo
             if ((rc = launch_unit(s, PROG_H2, 0, F_H2_REVERSE, sa, nullptr))) return rc;   // eo, ee
             if (fast) {
-                if ((rc = launch_odd_exchanged(s, PROG_ROT, F_REAL_ROT, sa))) return rc;
+                if ((rc = launch_exchanged(s, PROG_ROT, 1, F_REAL_ROT, sa, nullptr))) return rc;
                 return launch_unit(s, PROG_ROT, 0, F_REAL_ROT | F_MASK, sa, fuse_next ? sb_next : nullptr);
             }
             if ((rc = launch_sweep_flat(s, 1, F_REAL_ROT, sa))) return rc;
@@ -1127,7 +1139,7 @@ int join_side(ion_sim *s)
 bool obs_fusable(const ion_sim *s, uint32_t what)
 {
     const char *e = std::getenv("ION_NO_FUSED_OBS");  // A/B switch: every observed step on the single-sweep schedule + k_observe
-    if ((e && e[0] == '1') || !what || s->S != 1 || s->M != 4) return false;
+    if ((e && e[0] == '1') || !what || s->S != 1 || s->M != 4 || s->L_own != s->L_total) return false;
     if (what & ~(ION_OBS_NORM | ION_OBS_INNER_PRODUCTS | ION_OBS_NORM_BY_L | ION_OBS_R | ION_OBS_NORM_WITHIN)) return false;
     if (s->program == ION_SH_VEL_SO) return s->slab_state == 1 && s->slab_partial && s->slab_ip;
     if (s->program == ION_SH_LEN_SO) return s->len_fold_state == 1;
@@ -1388,12 +1400,18 @@ int ion_sim_create_sharded(int program, int64_t L_total, int64_t l_begin, int64_
     if (program == ION_SH_LEN_ADI && L_total > ion::ADI_CL * ion::ADI_MAX_THREADS)
         return fail(ION_ENOTSUP, "ION_SH_LEN_ADI: at most 4096 channels (one CTA holds all channels of a radial position)");
     const bool sharded = (L != L_total);
+    int cut_par = 0;
     if (sharded) {
         if (batch != 1) return fail(ION_ENOTSUP, "l-block shards hold one simulation (batch = 1)");
         if (program != ION_SH_LEN_SO && program != ION_SH_VEL_SO) return fail(ION_ENOTSUP, "l-block sharding: split-operator SphericalHarmonic programs only");
         if ((L_total % 2) != 0) return fail(ION_ENOTSUP, "l-block sharding needs an even l_bound");
-        if ((l_begin % 2) != 0 || (((l_begin + L) % 2) != 0 && l_begin + L != L_total))
-            return fail(ION_EINVAL, "l-block shards must begin and end on even channels (so that only odd sweeps cross a cut)");
+        const int64_t cut_lo = l_begin > 0 ? l_begin : -1, cut_hi = l_begin + L < L_total ? l_begin + L : -1;
+        const int par_lo = cut_lo >= 0 ? (int)(cut_lo & 1) : -1, par_hi = cut_hi >= 0 ? (int)(cut_hi & 1) : -1;
+        if (par_lo >= 0 && par_hi >= 0 && par_lo != par_hi) return fail(ION_EINVAL, "both cuts of an l-block shard must have the same parity");
+        cut_par = par_lo >= 0 ? par_lo : par_hi;
+        if (cut_par == 1 && program != ION_SH_LEN_SO)
+            return fail(ION_EINVAL, "l-block shards of this program must begin and end on even channels (so that only odd sweeps cross a cut); "
+                                    "odd cuts are for the length-gauge split-operator program");
     }
     if (ion_device_count() <= device || device < 0)
         return fail(ION_ENODEVICE, "no CUDA device " + std::to_string(device) + " (the engine has no CPU path)");
@@ -1418,6 +1436,7 @@ int ion_sim_create_sharded(int program, int64_t L_total, int64_t l_begin, int64_
     s->g_hi = (sharded && l_begin + L < L_total) ? 1 : 0;
     s->L_own = (int)L;
     s->l_own = (int)l_begin;
+    s->cut_parity = cut_par;
     s->L = (int)L + s->g_lo + s->g_hi;
     s->l_begin = (int)l_begin - s->g_lo;
     L = s->L;
@@ -1819,6 +1838,7 @@ int ion_sim_attach_peer(ion_sim_t *s, int side, const void *blob, int64_t blob_b
     s->peer_flags[side] = pblock;
     s->peer_stage[side] = reinterpret_cast<cplx *>(pblock + ion::HF_COUNT) + (size_t)facing * 2 * s->Rp;
     s->peers_attached = (!s->g_lo || s->peer_flags[0]) && (!s->g_hi || s->peer_flags[1]);
+    if (s->len_fold_state == -1) s->len_fold_state = 0;  // the folded length-gauge step of a shard needs the engine's own exchange: decide again
     s->invalidate_graphs();
     if (!s->side) {  // side branch for the exchange and the two boundary units of every odd-parity kernel (launch_odd_exchanged)
         CUDA_TRY(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
@@ -1844,6 +1864,11 @@ int ion_sim_prepare(ion_sim_t *s, double tau)
     if (int rc = ensure_factor(s, tau)) return rc;
     if (s->S > 1 || s->program == ION_SH_LEN_ADI)
         if (int rc = ensure_second_buffer(s)) return rc;
+    // linked shards must not allocate inside the step loop: decide the fused schedules (and their second buffer) here
+    if (s->L_own == s->L_total || s->peers_attached) {
+        if (int rc = slab_prepare(s)) return rc;
+        if (int rc = len_fold_prepare(s)) return rc;
+    }
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return ION_OK;
 }
@@ -1942,7 +1967,7 @@ int ion_sim_phase_needs_halo(ion_sim_t *s, int phase)
     Phase ph[8];
     const int n = phases_of(s, ph);
     if (phase < 0 || phase >= n) return 0;
-    return ph[phase].parity == 1 ? 1 : 0;  // shards are cut at even channels: only odd-parity pairs straddle a cut
+    return ph[phase].parity != s->cut_parity ? 1 : 0;  // pairs (l, l+1) with l % 2 == parity straddle a cut c when c % 2 != parity
 }
 
 int ion_sim_step_phase(ion_sim_t *s, int phase, double tau, const double *field)

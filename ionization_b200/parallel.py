@@ -5,11 +5,13 @@
   are gathered at the end (``gather_objects``).  The reference does the same with a process pool / HTCondor map
   (ionization_scans/scan_utils.py:638-663).
 
-* One very large SphericalHarmonicMesh simulation shards over contiguous l-blocks cut at EVEN channels.  The
+* One very large SphericalHarmonicMesh simulation shards over contiguous l-blocks.  Velocity gauge: cut at EVEN channels.  The
   Crank-Nicolson solve (in r) and every even-parity l-pair sweep are local to a shard; only the odd-parity sweeps
   couple the last channel of one shard to the first channel of the next, so before each odd-parity kernel the two
-  boundary channels are exchanged (1 exchange per step in the length gauge, 3 in the velocity gauge; one channel =
-  R * 16 bytes per direction) and both shards evaluate the straddling pair redundantly.  Two transports:
+  boundary channels are exchanged (3 exchanges per step; one channel = R * 16 bytes per direction) and both shards evaluate
+  the straddling pair redundantly.  Length gauge: cut at ODD channels -- every odd pair (and the solve) is local, and linked
+  shards run the engine's ONE-kernel step (PROG_LEN_STEP), whose read-only even-pair partners at either end of the block are the
+  ghost channels: 1 exchange and one pass over psi per step.  Two transports:
   ``attach_peers`` + ``step_device`` -- the production path: the engine's own kernel stores the boundary channel into the
   neighbour's ghost channel over NVLink peer memory (CUDA IPC mapping) with a flag hand-shake, inside the captured step
   loop, no host or NCCL call per step (csrc/halo.cuh); or ``step(..., exchanger)`` -- NCCL send/recv between phases
@@ -39,19 +41,25 @@ def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
     return begin, begin + base + (1 if rank < extra else 0)
 
 
-def l_block_partition(l_total: int, world_size: int) -> List[Tuple[int, int]]:
-    """[(l_begin, L)] per rank: contiguous blocks that begin (and, except the last, end) on EVEN channels, so that
-    only odd-parity pairs (2m+1, 2m+2) straddle a cut."""
+def l_block_partition(l_total: int, world_size: int, cut_parity: int = 0) -> List[Tuple[int, int]]:
+    """[(l_begin, L)] per rank: contiguous blocks cut at channels of one parity.
+
+    ``cut_parity=0``: blocks begin (and, except the last, end) on EVEN channels, so that only odd-parity pairs (2m+1, 2m+2)
+    straddle a cut -- every sharded program.  ``cut_parity=1`` (length gauge): blocks begin on ODD channels, every odd-parity
+    pair is local to a shard, and the engine's one-pass step (even rotations folded into the odd-pair Crank-Nicolson kernel, which
+    reads its even-pair partners read-only) runs on the shards with the ghost channels as those partners."""
     if l_total % 2:
         raise exceptions.UnsupportedConfiguration("l-block sharding needs an even l_bound")
     n_pairs = l_total // 2
     if world_size > n_pairs:
         raise exceptions.UnsupportedConfiguration(f"cannot cut {l_total} channels into {world_size} even blocks")
-    out = []
-    for r in range(world_size):
-        b, e = shard_range(n_pairs, r, world_size)
-        out.append((2 * b, 2 * (e - b)))
-    return out
+    cuts = [2 * shard_range(n_pairs, r, world_size)[0] for r in range(world_size)] + [l_total]
+    if cut_parity:
+        if world_size > 1 and (n_pairs - 1) < world_size:
+            raise exceptions.UnsupportedConfiguration(f"cannot cut {l_total} channels into {world_size} blocks at odd channels")
+        # the odd pairs (1,2) ... (l_total-3, l_total-2) are dealt out; channel 0 goes to the first block, l_total-1 to the last
+        cuts = [0] + [2 * shard_range(n_pairs - 1, r, world_size)[0] + 1 for r in range(1, world_size)] + [l_total]
+    return [(cuts[r], cuts[r + 1] - cuts[r]) for r in range(world_size)]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -116,13 +124,16 @@ class LocalExchanger:
 class ShardedSimulation:
     """The shard of ``problem`` (a dict of hot-path inputs, keys as in tests/golden/*.npz) owned by ``rank``."""
 
-    def __init__(self, problem, rank: int, world_size: int, device: int = 0, use_torch_stream: bool = True, radii=()):
+    def __init__(self, problem, rank: int, world_size: int, device: int = 0, use_torch_stream: bool = True, radii=(), cut_parity=None):
         kind = str(problem["kind"])
         if kind not in ("sh_len_so", "sh_vel_so"):
             raise exceptions.UnsupportedConfiguration("l-block sharding: split-operator SphericalHarmonic programs only")
         self.rank, self.world, self.device = rank, world_size, device
         L_total, R = int(problem["L"]), int(problem["R"])
-        self.l_begin, self.L = l_block_partition(L_total, world_size)[rank]
+        if cut_parity is None:  # length gauge: odd cuts, so that linked shards run the one-pass step (see l_block_partition)
+            cut_parity = 1 if (kind == "sh_len_so" and L_total // 2 - 1 >= world_size) else 0
+        self.cut_parity = int(cut_parity)
+        self.l_begin, self.L = l_block_partition(L_total, world_size, self.cut_parity)[rank]
         self.L_total, self.R = L_total, R
         eng = _engine.DeviceSimulation(kind, self.L, R, batch=1, device=device, L_total=L_total, l_begin=self.l_begin)
         self.engine = eng

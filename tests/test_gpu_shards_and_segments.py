@@ -9,10 +9,10 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
 
-def _run_sharded(p, world, n_steps=None, what=0):
+def _run_sharded(p, world, n_steps=None, what=0, cut_parity=None):
     from ionization_b200 import parallel
 
-    shards = [parallel.ShardedSimulation(p, r, world, device=0, use_torch_stream=False) for r in range(world)]
+    shards = [parallel.ShardedSimulation(p, r, world, device=0, use_torch_stream=False, cut_parity=cut_parity) for r in range(world)]
     ex = parallel.LocalExchanger(shards)
     taus, fields = p["taus"][:n_steps], p["fields"][:n_steps]
     import torch
@@ -76,6 +76,35 @@ def test_l_block_shards_equal_unsharded_run_on_a_larger_mesh(kind):
     assert rel_err(g, g_ref) < 1e-12
 
 
+@pytest.mark.parametrize("cut_parity", [0, 1])
+@pytest.mark.parametrize("transport", ["phases", "device"])
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_length_gauge_shards_with_even_and_odd_cuts(cut_parity, transport, world):
+    """length gauge: blocks cut at even channels (the straddling odd pairs are evaluated on both sides, single-sweep kernels) and
+    at odd channels (every odd pair local; linked shards run the one-kernel folded step with the ghost channels as the read-only
+    even-pair partners) against the reference fixture, observables included"""
+    from ionization_b200 import _native as nat
+
+    p = load_golden("sh_len_so_datastores_120x12")
+    what = nat.OBS_NORM | nat.OBS_INNER_PRODUCTS | nat.OBS_NORM_BY_L | nat.OBS_R | nat.OBS_Z
+    run = _run_sharded if transport == "phases" else _run_sharded_device
+    g, rec = run(p, world, what=what, cut_parity=cut_parity)
+    assert rel_err(g, p["g_final"]) < TOL
+    ns, L = len(p["state_l"]), int(p["L"])
+    assert abs(rec[0] - p["norm"][-1]) < TOL
+    c = 1 + 2 * ns
+    assert np.max(np.abs(rec[c : c + L] - p["norm_by_l"][-1])) < TOL
+    assert abs(rec[c + L] - p["r_expectation"][-1]) < TOL * abs(p["r_expectation"][-1])
+    assert abs(rec[c + L + 1] - p["z_expectation"][-1]) < TOL * abs(p["r_expectation"][-1])
+
+
+def test_odd_cuts_are_refused_for_the_velocity_gauge():
+    from ionization_b200 import engine, exceptions
+
+    with pytest.raises(exceptions.IonizationException):
+        engine.DeviceSimulation("sh_vel_so", 4, 64, batch=1, device=0, L_total=12, l_begin=3)
+
+
 @pytest.mark.parametrize("kind", ["LEN", "VEL"])
 @pytest.mark.parametrize("R", [5000, 4609])
 def test_r_segmented_kernels_match_oracle(kind, R):
@@ -124,7 +153,7 @@ def test_segmented_line_split_operator_long_mesh():
         assert rel_err(g, ref) < TOL, kind
 
 
-def _run_sharded_device(p, world, n_steps=None, what=0):
+def _run_sharded_device(p, world, n_steps=None, what=0, cut_parity=None):
     """the production transport: shards linked with ion_sim_attach_peer, advanced by the device-resident loop with the
     engine's own halo-exchange kernel (flags + stores into the neighbour's ghost channel).  Several shards in ONE process
     on one GPU: every shard is driven from its own host thread, as every rank would be from its own process."""
@@ -132,7 +161,7 @@ def _run_sharded_device(p, world, n_steps=None, what=0):
 
     from ionization_b200 import parallel
 
-    shards = [parallel.ShardedSimulation(p, r, world, device=0, use_torch_stream=False) for r in range(world)]
+    shards = [parallel.ShardedSimulation(p, r, world, device=0, use_torch_stream=False, cut_parity=cut_parity) for r in range(world)]
     parallel.ShardedSimulation.attach_local(shards)
     taus, fields = p["taus"][:n_steps], p["fields"][:n_steps]
     for s in shards:

@@ -33,6 +33,22 @@ def test_l_block_partition_cuts_at_even_channels():
         parallel.l_block_partition(4, 3)
 
 
+def test_l_block_partition_cuts_at_odd_channels():
+    """length gauge: every odd pair (2m+1, 2m+2) stays inside one block; channel 0 and the last channel go to the end blocks"""
+    for L in (10, 200, 500, 4096):
+        for w in (1, 2, 4, 5):
+            if L // 2 - 1 < w and w > 1:
+                continue
+            blocks = parallel.l_block_partition(L, w, cut_parity=1)
+            assert blocks[0][0] == 0 and sum(n for _, n in blocks) == L
+            for (b0, n0), (b1, _) in zip(blocks[:-1], blocks[1:]):
+                assert b0 + n0 == b1 and b1 % 2 == 1
+            sizes = [n for _, n in blocks]
+            assert max(sizes) - min(sizes) <= 3
+    with pytest.raises(Exception):
+        parallel.l_block_partition(4, 2, cut_parity=1)
+
+
 def test_combine_observations():
     what = nat.OBS_NORM | nat.OBS_INNER_PRODUCTS | nat.OBS_NORM_BY_L | nat.OBS_R
     a = np.array([0.25, 1.0, 2.0, 0.0, 0.0, 0.1, 0.15, 3.0])  # norm, ip0(re,im), ip1, nbl x2, r
