@@ -167,6 +167,48 @@ ION_DEVINL cplx ld_c(const cplx *p) { return *p; }
 ION_DEVINL void st_c(cplx *p, cplx v) { *p = v; }
 
 // ---------------------------------------------------------------------------------------------
+// l-block shards: flags and spin-waits of the peer-memory halo exchange (halo.cuh: the stand-alone exchange kernel;
+// kernels.cuh: the exchange fused into the folded length-gauge step, PROG_LEN_STEP_HALO)
+// ---------------------------------------------------------------------------------------------
+// halo block of a shard: HF_COUNT flags (unsigned long long), then staging[side][slot][n] complex values for the exchange kernel,
+// then fstage[side][slot][n] for the fused exchange (separate slots: the two mechanisms interleave at chunk boundaries)
+namespace ion {
+enum : int { HF_ARRIVE = 2, HF_SEQ = 4, HF_DONE = 5, HF_DONE_SIDE = 6, HF_ABORT = 8, HF_FARRIVE = 10, HF_COUNT = 16 };
+}
+using namespace ion;
+
+ION_DEVINL void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+ION_DEVINL void red_release_sys_add(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+ION_DEVINL unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// thread 0 of a CTA waits for *p >= k; returns false on time-out / abort
+ION_DEVINL bool halo_spin(const unsigned long long *p, unsigned long long k, unsigned long long *flags, long long limit)
+{
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    while (ld_acquire_sys(p) < k) {
+        if ((++spins & 63u) == 0u) {
+            if (ld_acquire_sys(flags + HF_ABORT) != 0ull) return false;
+            if (clock64() - t0 > limit) {
+                st_release_sys(flags + HF_ABORT, 1ull);
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Affine-map scans.  Thread t carries the map f_t(v) = P_t * v + B_t.
 // FWD:  value entering thread t is (f_{t-1} o ... o f_0)(0)
 // !FWD: value entering thread t is (f_{t+1} o ... o f_{T-1})(0)        (reverse direction)

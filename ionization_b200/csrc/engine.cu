@@ -549,7 +549,7 @@ int ensure_factor(ion_sim *s, double tau)
         const int nw = s->T / 32, n = s->L * nw;
         double *d_bound = nullptr;
         if (int rc = dev_alloc(&d_bound, (size_t)n)) return rc;
-        ion::k_scan_bound<<<(n + 127) / 128, 128, 0, s->stream>>>(s->aggP, s->aggQ, s->L, s->T, d_bound);
+        ion::k_scan_bound<<<(n + 127) / 128, 128, 0, s->stream>>>(s->aggP, s->aggQ, s->L, s->T, 32, d_bound);
         std::vector<double> hb((size_t)n);
         cudaError_t e = cudaMemcpyAsync(hb.data(), d_bound, hb.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
@@ -600,7 +600,27 @@ int ensure_factor(ion_sim *s, double tau)
             // r-segments: the halo must cover the reach; programs with r-pair bricks (velocity gauge) get one more warp of
             // margin per unit of reach for the brick edge effects
             const bool bricks = (s->program == ION_SH_VEL_SO || s->program == ION_LINE_VEL_SO);
-            const int H = (bricks ? 64 : 32) * reach;
+            int H = (bricks ? 64 : 32) * reach;
+            if (s->program == ION_SH_LEN_SO && reach == 1 && s->T_seg % 32 == 0) {
+                // half-warp halos: the product of the multipliers over any aligned 16 threads (64 rows) is below 1e-18, i.e. what a
+                // segment ignores of its neighbour is two orders below the rounding of the values it would multiply
+                const char *env = std::getenv("ION_HALO16");
+                if (!(env && env[0] == '0')) {
+                    const int ng = s->T / 16, n = s->L * ng;
+                    double *d_bound = nullptr;
+                    if (int rc = dev_alloc(&d_bound, (size_t)n)) return rc;
+                    ion::k_scan_bound<<<(n + 127) / 128, 128, 0, s->stream>>>(s->aggP, s->aggQ, s->L, s->T, 16, d_bound);
+                    std::vector<double> hb((size_t)n);
+                    cudaError_t e = cudaMemcpyAsync(hb.data(), d_bound, hb.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+                    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+                    cudaFree(d_bound);
+                    if (e != cudaSuccess) return fail(ION_ECUDA, std::string("k_scan_bound: ") + cudaGetErrorString(e));
+                    double mx16 = -1e300;
+                    for (double v : hb) mx16 = std::max(mx16, v);
+                    if (mx16 < std::log(1e-18)) H = 16;
+                    if (std::getenv("ION_DEBUG")) std::fprintf(stderr, "[ion] r-segments: multipliers over 16 threads <= %.3g, halo %d threads\n", std::exp(mx16), H);
+                }
+            }
             if (reach == 0 || s->T_seg + 2 * H > 512)
                 return fail(ION_ENOTSUP,
                             "r_points > 4096 needs the Crank-Nicolson LU multipliers to decay below 1e-30 within the segment halo; this "
@@ -1435,7 +1455,9 @@ int ion_sim_create_sharded(int program, int64_t L_total, int64_t l_begin, int64_
         // split-operator step (32-thread halos) takes 192-thread segments instead: 256-thread CTAs, two per SM at 128 registers,
         // whose load / solve / store phases overlap -- 33 % recomputed rows instead of 17 %, and still 7 % faster on the
         // HBM-resident 16384 x 4096 mesh (1274 -> 1180 us per step; 160: 1275, 256: 1548, 320: 1346)
-        T_seg = (program == ION_SH_LEN_SO) ? 192 : 384;
+        // With half-warp halos (ensure_factor: the multipliers decay below 1e-18 over 64 rows) the same 256-thread CTA holds 224
+        // interior threads: 14 % recomputed rows.
+        T_seg = (program == ION_SH_LEN_SO) ? 224 : 384;
         if (const char *env = std::getenv("ION_TSEG")) {  // A/B switch
             const int v = std::atoi(env);
             if (v >= 64 && v <= 384 && v % 32 == 0) T_seg = v;

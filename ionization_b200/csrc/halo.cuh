@@ -22,9 +22,6 @@
 
 namespace ion {
 
-// halo block of a shard: HF_COUNT flags (unsigned long long), then staging[side][slot][n] complex values
-enum : int { HF_ARRIVE = 2, HF_SEQ = 4, HF_DONE = 5, HF_DONE_SIDE = 6, HF_ABORT = 8, HF_COUNT = 16 };
-
 struct HaloParams {
     unsigned long long *flags;          // my flag block [HF_COUNT]
     unsigned long long *peer_flags[2];  // the neighbours' flag blocks (nullptr: no neighbour on that side)
@@ -35,33 +32,6 @@ struct HaloParams {
     long long n;                        // complex values per channel (Rp * batch)
     long long spin_limit;               // clock64 ticks before a wait gives up
 };
-
-ION_DEVINL void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-ION_DEVINL unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-// thread 0 of a CTA waits for *p >= k; returns false on time-out / abort
-ION_DEVINL bool halo_spin(const unsigned long long *p, unsigned long long k, unsigned long long *flags, long long limit)
-{
-    const long long t0 = clock64();
-    unsigned spins = 0;
-    while (ld_acquire_sys(p) < k) {
-        if ((++spins & 63u) == 0u) {
-            if (ld_acquire_sys(flags + HF_ABORT) != 0ull) return false;
-            if (clock64() - t0 > limit) {
-                st_release_sys(flags + HF_ABORT, 1ull);
-                return false;
-            }
-        }
-    }
-    return true;
-}
 
 // grid = (n_ctas, 2 sides), block = 256
 __global__ void __launch_bounds__(256) k_halo_exchange(const HaloParams p)

@@ -65,6 +65,16 @@ struct UnitParams {
     unsigned obs_what;
     double vec_dv;           // != 0: vec is linear in the row index with this increment per row (length gauge on the uniform radial grid)
     int unit0, unit_stride;  // unit of CTA x = unit0 + x * unit_stride (0, 1: all units; the ensemble kernel leaves the single channels to k_unit)
+    // PROG_LEN_STEP_HALO: the folded step of an l-block shard cut at odd channels with the halo exchange fused in (see k_unit)
+    unsigned long long *hf_flags;          // my flag block (common.cuh: HF_*)
+    unsigned long long *hf_peer_flags[2];  // the neighbours' flag blocks (peer memory)
+    cplx *hf_peer_fstage[2];               // the neighbour's two fused staging slots for the side facing me (peer memory)
+    const cplx *hf_my_fstage[2];           // my two fused staging slots for side 0 (lower) / 1 (upper)
+    unsigned long long *hf_sent;           // [2][S]: launches so far, kept by the boundary CTA (side, segment)
+    long long hf_spin_limit;
+    int hf_unit[2];                        // the unit whose even-pair partner is the lower / upper ghost channel (-1: no neighbour)
+    int hf_consume;                        // the ghost channels of this launch are the previous launch's deliveries (else: already in psi)
+    int n_units, boundary_first;           // boundary_first: CTA order (first unit, last unit, interior units) instead of ascending
 };
 
 // unit -> (first local channel, is pair).  Pairs are (l, l+1) with global l % 2 == parity.
@@ -95,6 +105,13 @@ ION_DEVINL void load_rows(cplx (&g)[M], const cplx *base, int T, int t, bool ok)
 {
 #pragma unroll
     for (int k = 0; k < M; ++k) g[k] = ok ? ld_c(base + k * T + t) : c_zero();
+}
+// the same through L2 only (data another GPU stored into this one's memory while the kernel may already be running)
+template <int M>
+ION_DEVINL void load_rows_cg(cplx (&g)[M], const cplx *base, int T, int t, bool ok)
+{
+#pragma unroll
+    for (int k = 0; k < M; ++k) g[k] = ok ? __ldcg(reinterpret_cast<const double2 *>(base + k * T + t)) : c_zero();
 }
 template <int M>
 ION_DEVINL void store_rows(const cplx (&g)[M], cplx *base, int T, int t, bool ok)
@@ -510,6 +527,9 @@ enum : int {
                          // then rotation(s_a), CN, rotation(s_a) on the odd pair; out of place -- one pass per LEN step
     PROG_LEN_STEP_OBS = 9,  // the same with the observation of the PREVIOUS step fused in: even rotation(s_b), mask, reductions over
                             // the unit's own channels, even rotation(s_a), ... (north_star 4; see obs_channel)
+    PROG_LEN_STEP_HALO = 10,  // PROG_LEN_STEP of an l-block shard cut at odd channels with the halo exchange FUSED in: the CTAs of the
+                              // block's first / last pair store their boundary channel into the neighbour's memory over NVLink
+                              // (epilogue) and read their ghost partner from the slot the neighbour filled one step earlier (prologue)
 };
 
 // One member of an l-pair rotation [[c, -i s], [-i s, c]] (the matrix is symmetric: both members use the same formula)
@@ -687,6 +707,8 @@ ION_DEVINL void line_cn_factors(CnFactors<M> &f, const cplx (&D)[M], const doubl
 // swaps the buffers): in place, a CTA of a later wave would read rows its neighbour has already advanced.  That is exact to < 1e-30
 // because the LU multipliers decay geometrically -- the host verifies (k_scan_bound) that their product over any 32
 // threads is below 1e-30 before it allows S > 1.  Halo results are discarded; only interior threads store.
+// The length-gauge programs (no r-pair bricks) take HALF-WARP halos (16 threads = 64 rows) when the product over any aligned
+// 16 threads is below 1e-18 -- two orders below the rounding of the values it multiplies: 224 interior threads of 256.
 template <int M, int PROG, int TMAX, bool SEG>
 #ifndef ION_PAIR_MINB
 #define ION_PAIR_MINB 1
@@ -702,7 +724,11 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
     const int tl = threadIdx.x, Tc = blockDim.x;         // index inside the CTA: scans and exchanges
     const int T = p.T;                                   // row stride of the layout
     // SEG == false (one CTA per channel, the common case): all of this folds away at compile time
-    const int seg = SEG ? (int)(blockIdx.x % p.S) : 0, unit = p.unit0 + (SEG ? (int)(blockIdx.x / p.S) : (int)blockIdx.x) * p.unit_stride;
+    const int seg = SEG ? (int)(blockIdx.x % p.S) : 0;
+    int ux = SEG ? (int)(blockIdx.x / p.S) : (int)blockIdx.x;
+    // boundary units first: what they send is under way long before the neighbour's next launch asks for it
+    if (PROG == PROG_LEN_STEP_HALO && p.boundary_first) ux = ux == 0 ? 0 : (ux == 1 ? p.n_units - 1 : ux - 1);
+    const int unit = p.unit0 + ux * p.unit_stride;
     const int t = SEG ? seg * p.T_seg - p.H + tl : tl;   // thread index inside the channel: addressing
     const bool ok = SEG ? ((t >= 0) && (t < T)) : true;
     const bool mine = SEG ? (ok && (tl >= p.H) && (tl < p.H + p.T_seg)) : true;
@@ -778,7 +804,8 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
 
     // ---- programs containing Crank-Nicolson ----
     // pairs: both channels are solved together in layout 2 (see above); single channels and r-segments keep layout 1
-    constexpr bool LENSTEP = (PROG == PROG_LEN_STEP || PROG == PROG_LEN_STEP_OBS), OBS = (PROG == PROG_LEN_STEP_OBS);
+    constexpr bool LENSTEP = (PROG == PROG_LEN_STEP || PROG == PROG_LEN_STEP_OBS || PROG == PROG_LEN_STEP_HALO), OBS = (PROG == PROG_LEN_STEP_OBS);
+    constexpr bool HALO = (PROG == PROG_LEN_STEP_HALO);
     // (r-segments included: the thread's position in the channel is t = segment offset + tl, halo threads beyond either end of the
     // channel -- !ok -- carry identity factors and zero multipliers, and the recurrences start from zero at the edge of the halo)
     constexpr bool L2CN = (M == 4) && (TMAX <= 512) && (PROG == PROG_ROT_CN_ROT || PROG == PROG_H2_CN_H2 || LENSTEP);
@@ -869,6 +896,8 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         ION_CK(1);
         pdl_wait();
         ION_CK(2);
+        bool blo = false, bhi = false;    // HALO: this CTA's pair reads the lower / upper ghost channel and sends the boundary channel
+        unsigned long long ksent = 0ull;  // HALO: launches so far
         load_rows<M>(A, base, T, t, ok);
         load_rows<M>(B, base + chan, T, t, ok);
 #ifndef ION_H2_TRIG_FIRST
@@ -897,9 +926,39 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
             rotate_member<M>(B, Q, rot_angles_auto<M>(cvec, p.vec_dv, sa * p.cl[p.l_begin + l0 + 1]));
         } else if (LENSTEP) {
             cplx Q[M];
-            load_rows<M>(Q, base - chan, T, t, ok);
+            const cplx *qlo = base - chan, *qhi = base + 2 * chan;
+            if constexpr (HALO) {
+                // FUSED HALO EXCHANGE, receiving side.  k = launches of this program so far (every launch sends, so the neighbour's
+                // arrival counter after its launch k-1 is S * k); the ghost partner is in the slot (k-1) & 1 the neighbour's launch
+                // k-1 stored into.  No hand-shake for the slot's reuse: the neighbour's launch k+1 overwrites it only after it has seen
+                // the S arrivals of MY launch k, which every CTA of mine sends after its reads.
+                blo = (unit == p.hf_unit[0]), bhi = (unit == p.hf_unit[1]);
+                if (blo || bhi) {
+                    ksent = p.hf_sent[(blo ? 0 : 1) * p.S + seg];
+                    if (p.hf_consume) {
+                        __shared__ int hf_ok;
+                        if (tl == 0) {
+                            const unsigned long long need = (unsigned long long)p.S * ksent;
+                            bool good = true;
+                            if (blo) good = halo_spin(p.hf_flags + HF_FARRIVE + 0, need, p.hf_flags, p.hf_spin_limit);
+                            if (bhi && good) good = halo_spin(p.hf_flags + HF_FARRIVE + 1, need, p.hf_flags, p.hf_spin_limit);
+                            if (!good)  // tell both neighbours: they must not keep stepping with a ghost channel that never arrived here
+                                for (int q = 0; q < 2; ++q)
+                                    if (p.hf_peer_flags[q]) st_release_sys(p.hf_peer_flags[q] + HF_ABORT, 1ull);
+                            hf_ok = good ? 1 : 0;
+                        }
+                        __syncthreads();
+                        const size_t slot = (size_t)((ksent + 1ull) & 1ull) * chan;
+                        if (blo) qlo = p.hf_my_fstage[0] + slot;
+                        if (bhi) qhi = p.hf_my_fstage[1] + slot;
+                    }
+                }
+            }
+            if (HALO && blo && p.hf_consume) load_rows_cg<M>(Q, qlo, T, t, ok);
+            else load_rows<M>(Q, qlo, T, t, ok);
             rotate_member<M>(A, Q, eangA);
-            load_rows<M>(Q, base + 2 * chan, T, t, ok);
+            if (HALO && bhi && p.hf_consume) load_rows_cg<M>(Q, qhi, T, t, ok);
+            else load_rows<M>(Q, qhi, T, t, ok);
             rotate_member<M>(B, Q, eangB);
             if (p.flags & F_MASK) {
                 double mk[M];
@@ -929,6 +988,27 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         ION_CK(6);
         store_rows<M>(A, obase, T, t, mine);
         store_rows<M>(B, obase + chan, T, t, mine);
+        if constexpr (HALO) {
+            // FUSED HALO EXCHANGE, sending side: the block's first channel goes to the lower neighbour, its last channel to the upper
+            // one -- straight from the registers that hold the result, into the neighbour's slot k & 1, then ONE arrival per CTA
+            if (blo || bhi) {
+                const size_t slot = (size_t)(ksent & 1ull) * chan;
+                if (blo && p.hf_peer_fstage[0]) store_rows<M>(A, p.hf_peer_fstage[0] + slot, T, t, mine);
+                if (bhi && p.hf_peer_fstage[1]) store_rows<M>(B, p.hf_peer_fstage[1] + slot, T, t, mine);
+                __threadfence_system();
+                __syncthreads();
+                if (tl == 0) {
+                    if (blo) {
+                        if (p.hf_peer_flags[0]) red_release_sys_add(p.hf_peer_flags[0] + HF_FARRIVE + 1, 1ull);
+                        p.hf_sent[0 * p.S + seg] = ksent + 1ull;
+                    }
+                    if (bhi) {
+                        if (p.hf_peer_flags[1]) red_release_sys_add(p.hf_peer_flags[1] + HF_FARRIVE + 0, 1ull);
+                        p.hf_sent[1 * p.S + seg] = ksent + 1ull;
+                    }
+                }
+            }
+        }
         ION_CK(7);
 #ifdef ION_EXP_CLOCKS
         if ((tl == 0 || tl == 288) && (blockIdx.x == 3 || blockIdx.x == 200) && blockIdx.y == 0)
@@ -1247,16 +1327,17 @@ __global__ void k_make_th(const cplx *__restrict__ h_diag, double tau, int R, in
     th[pos] = (i < R) ? c_scale(h_diag[i], tau) : c_zero();
 }
 
-// log-magnitude of the product of the chunk multipliers over each warp (32 consecutive threads): the host takes
-// the maximum to decide whether the cross-warp part of the CN scans is short-ranged (common.cuh).
-__global__ void k_scan_bound(const cplx *__restrict__ aggP, const cplx *__restrict__ aggQ, int L, int T, double *__restrict__ out)
+// log-magnitude of the product of the chunk multipliers over each group of G consecutive threads (G = 32: a warp): the host
+// takes the maximum to decide whether the cross-warp part of the CN scans is short-ranged (common.cuh), and whether a
+// half-warp halo (G = 16) is enough for the r-segments of the length gauge.
+__global__ void k_scan_bound(const cplx *__restrict__ aggP, const cplx *__restrict__ aggQ, int L, int T, int G, double *__restrict__ out)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (l, warp)
-    const int nw = T / 32;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (l, group)
+    const int nw = T / G;
     if (idx >= L * nw) return;
     const int l = idx / nw, w = idx % nw;
     double sp = 0.0, sq = 0.0;
-    for (int t = w * 32; t < w * 32 + 32; ++t) {
+    for (int t = w * G; t < w * G + G; ++t) {
         sp += 0.5 * log(fmax(c_abs2(aggP[(size_t)l * T + t]), 1e-300));
         sq += 0.5 * log(fmax(c_abs2(aggQ[(size_t)l * T + t]), 1e-300));
     }
