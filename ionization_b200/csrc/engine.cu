@@ -113,6 +113,11 @@ struct ion_sim {
     unsigned long long *hflags = nullptr;           // my halo block: HF_COUNT flags, then staging[2 sides][2 slots][Rp]
     unsigned long long *peer_flags[2] = {nullptr, nullptr};
     cplx *peer_stage[2] = {nullptr, nullptr};       // the neighbours' staging slots facing this shard (peer mappings)
+    // exchange fused into the folded length-gauge step (kernels.cuh: PROG_LEN_STEP_HALO): the neighbours' fused staging slots
+    // facing this shard, and the per-(side, segment) launch counters of the boundary CTAs
+    cplx *peer_fstage[2] = {nullptr, nullptr};
+    unsigned long long *hf_sent = nullptr;
+    bool use_fused_halo = true;
     void *peer_ipc_base[2] = {nullptr, nullptr};    // IPC mappings to close
     bool peers_attached = false;
     bool neighbour_on_same_device = false;  // a linked neighbour lives on this GPU (several shards of one process on one device)
@@ -206,6 +211,7 @@ struct ion_sim {
         for (void *q : peer_ipc_base)
             if (q) cudaIpcCloseMemHandle(q);
         if (hflags) cudaFree(hflags);
+        if (hf_sent) cudaFree(hf_sent);
         for (int k = 0; k < 2; ++k) {
             if (scal_host[k]) cudaFreeHost(scal_host[k]);
             if (scal_ev[k]) cudaEventDestroy(scal_ev[k]);
@@ -278,7 +284,7 @@ void prof_end(ion_sim *s)
 size_t unit_smem_bytes(const ion_sim *s, int prog = -1)
 {
     size_t n = (256 + 4 * (size_t)s->Tc) * sizeof(cplx);
-    const bool cn_pair = (prog == ion::PROG_ROT_CN_ROT || prog == ion::PROG_H2_CN_H2 || prog == ion::PROG_LEN_STEP || prog == ion::PROG_LEN_STEP_OBS || prog < 0);
+    const bool cn_pair = (prog == ion::PROG_ROT_CN_ROT || prog == ion::PROG_H2_CN_H2 || prog == ion::PROG_LEN_STEP || prog == ion::PROG_LEN_STEP_OBS || prog == ion::PROG_LEN_STEP_HALO || prog < 0);
     if (cn_pair && s->M == 4 && s->tmax <= 512) n += 8 * (size_t)s->Tc * sizeof(cplx) + 9 * (size_t)(s->Tc / 2) * sizeof(double);
     return n;
 }
@@ -319,7 +325,7 @@ template <int PROG>
 int set_unit_smem_attr()
 {
     CUDA_TRY(cudaFuncSetAttribute(ion::k_unit<4, PROG, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    if (PROG == ion::PROG_ROT_CN_ROT || PROG == ion::PROG_H2_CN_H2 || PROG == ion::PROG_LEN_STEP || PROG == ion::PROG_LEN_STEP_OBS) {
+    if (PROG == ion::PROG_ROT_CN_ROT || PROG == ion::PROG_H2_CN_H2 || PROG == ion::PROG_LEN_STEP || PROG == ion::PROG_LEN_STEP_OBS || PROG == ion::PROG_LEN_STEP_HALO) {
         CUDA_TRY(cudaFuncSetAttribute(ion::k_unit<4, PROG, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(ion::k_unit<4, PROG, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(ion::k_unit<4, PROG, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
@@ -336,7 +342,8 @@ int prepare_kernels(ion_sim *s)
         (rc = set_unit_smem_attr<ion::PROG_H2>()) || (rc = set_unit_smem_attr<ion::PROG_H2_CN_H2>()) ||
         (rc = set_unit_smem_attr<ion::PROG_CN>()) || (rc = set_unit_smem_attr<ion::PROG_LINE_SO_LEN>()) ||
         (rc = set_unit_smem_attr<ion::PROG_LINE_SO_VEL>()) || (rc = set_unit_smem_attr<ion::PROG_LINE_CN>()) ||
-        (rc = set_unit_smem_attr<ion::PROG_LEN_STEP>()) || (rc = set_unit_smem_attr<ion::PROG_LEN_STEP_OBS>()))
+        (rc = set_unit_smem_attr<ion::PROG_LEN_STEP>()) || (rc = set_unit_smem_attr<ion::PROG_LEN_STEP_OBS>()) ||
+        (rc = set_unit_smem_attr<ion::PROG_LEN_STEP_HALO>()))
         return rc;
     return ION_OK;
 }
@@ -385,7 +392,7 @@ int launch_observe_finish(ion_sim *s, uint32_t what, double *dev_out);
 // a subset of the units of a launch: units sub_unit0 + k * sub_stride, k < sub_count (sub_count == 0: all units).  do_swap = false:
 // an out-of-place kernel leaves the buffer swap to the launch that covers the remaining units
 int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, const double *sb, uint32_t obs_what = 0, int sub_unit0 = 0, int sub_stride = 1,
-                int sub_count = 0, bool do_swap = true)
+                int sub_count = 0, bool do_swap = true, int halo_consume = 0)
 {
     ion::UnitParams p = base_params(s);
     p.parity = parity;
@@ -415,7 +422,7 @@ int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, c
     if (prog == ion::PROG_ROT) p.H = 0;  // point-wise in r: interior threads only
     // r-segments: a kernel that reads halo rows (every program but the point-wise rotation) must not run in place
     // the ADI solve goes back to the buffer the l-pass read from, so that a step ends where it began
-    const bool seg_oop = (s->S > 1 && prog != ion::PROG_ROT && prog != ion::PROG_LEN_STEP && prog != ion::PROG_LEN_STEP_OBS) || (prog == ion::PROG_CN && (flags & ion::F_SOLVE_ONLY));
+    const bool seg_oop = (s->S > 1 && prog != ion::PROG_ROT && prog != ion::PROG_LEN_STEP && prog != ion::PROG_LEN_STEP_OBS && prog != ion::PROG_LEN_STEP_HALO) || (prog == ion::PROG_CN && (flags & ion::F_SOLVE_ONLY));
     if (seg_oop) {
         if (!s->psi2) return fail(ION_ESTATE, "internal: second wavefunction buffer missing for a segmented kernel");
         p.psi_out = s->psi2;
@@ -473,6 +480,29 @@ int launch_unit(ion_sim *s, int prog, int parity, int flags, const double *sa, c
             }
             if (do_swap) std::swap(s->psi, s->psi2);
             break;
+        case ion::PROG_LEN_STEP_HALO: {  // linked l-block shard cut at odd channels: the folded step with the halo exchange fused in
+            kind = KK_LEN_STEP;
+            p.psi_out = s->psi2;
+            const size_t chan = (size_t)s->Rp;
+            cplx *fstage = reinterpret_cast<cplx *>(s->hflags + ion::HF_COUNT) + 4 * chan;  // [2 sides][2 slots][Rp], behind the exchange kernel's slots
+            p.hf_flags = s->hflags;
+            for (int side = 0; side < 2; ++side) {
+                p.hf_peer_flags[side] = s->peer_flags[side];
+                p.hf_peer_fstage[side] = s->peer_fstage[side];
+                p.hf_my_fstage[side] = fstage + (size_t)side * 2 * chan;
+            }
+            p.hf_sent = s->hf_sent;
+            p.hf_spin_limit = 20000000000ll;  // ~10 s of SM clock
+            p.hf_unit[0] = s->g_lo ? p.unit0 : -1;
+            p.hf_unit[1] = s->g_hi ? p.unit0 + (units - 1) * p.unit_stride : -1;
+            p.hf_consume = halo_consume;
+            p.n_units = units;
+            p.boundary_first = units >= 2 ? 1 : 0;
+            prof_begin(s, kind);
+            rc = launch_unit_prog<ion::PROG_LEN_STEP_HALO>(s, p, grid);
+            if (do_swap) std::swap(s->psi, s->psi2);
+            break;
+        }
         case ion::PROG_LEN_STEP_OBS:  // never the persistent ensemble kernel: the observed step runs one CTA per (unit, member)
             kind = KK_LEN_STEP;
             p.psi_out = s->psi2;
@@ -910,7 +940,18 @@ int launch_exchange(ion_sim *s)
 // inside a stream capture (the event record / wait pairs become graph edges).  Used when every neighbour lives on another device
 // (one shard per GPU): with several shards on ONE device a spinning exchange kernel at the head of a hardware work queue can hold
 // back another shard's kernels that the driver mapped to the same queue, so those (tests, devices=[0, 0, ..]) keep one stream per shard.
-int launch_exchanged(ion_sim *s, int prog, int parity, int flags, const double *sa, const double *sb)
+bool fused_halo_ok(const ion_sim *s)
+{
+    // neighbours on this device (several shards of one process on one GPU: tests) keep the stand-alone exchange unless asked
+    // (ION_FUSED_HALO=1): a CTA that spins for a neighbour's kernel shares the device with that kernel there
+    const char *env = std::getenv("ION_FUSED_HALO");
+    if (env && env[0] == '0') return false;
+    if (s->neighbour_on_same_device && !(env && env[0] == '1')) return false;
+    // the exchange lives in the layout-2 pair path of k_unit (CTAs of at most 512 threads; r-segments always are)
+    return s->use_fused_halo && s->peers_attached && s->cut_parity == 1 && s->M == 4 && (s->S > 1 || s->tmax <= 512) && s->hf_sent && !s->profiling;
+}
+
+int launch_exchanged(ion_sim *s, int prog, int parity, int flags, const double *sa, const double *sb, bool consume = false)
 {
     const bool folded = (prog == ion::PROG_LEN_STEP);
     if (!s->peers_attached || (!folded && parity == s->cut_parity)) return launch_unit(s, prog, parity, flags, sa, sb);
@@ -918,6 +959,14 @@ int launch_exchanged(ion_sim *s, int prog, int parity, int flags, const double *
     const int units_all = ion::num_units(s->L, s->l_begin, parity);
     const int u0 = folded ? s->g_lo : 0, u1 = units_all - 1 - (folded ? s->g_hi : 0);
     const int units = u1 - u0 + 1;
+    if (folded && fused_halo_ok(s)) {
+        // the exchange rides inside the step kernel: launch k stores its boundary channels into the neighbours' slots k & 1 and
+        // reads its ghost partners from the slots the neighbours' launch k - 1 filled.  `consume` == false (the first folded step
+        // after anything else): the ghost channels come from the stand-alone exchange, as before; the launch still sends.
+        if (!consume)
+            if (int rc = launch_exchange(s)) return rc;
+        return launch_unit(s, ion::PROG_LEN_STEP_HALO, parity, flags, sa, sb, 0, u0, 1, units, true, consume ? 1 : 0);
+    }
     const char *env = std::getenv("ION_SERIAL_EXCHANGE");
     if (!s->side || units < 3 || s->profiling || (env && env[0] == '1') || s->neighbour_on_same_device) {
         if (int rc = launch_exchange(s)) return rc;
@@ -965,7 +1014,7 @@ int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, int pre, b
                     rc = launch_observe_finish(s, prev.what, prev.dst);
                     prof_end(s);
                     if (rc) return rc;
-                } else if ((rc = launch_exchanged(s, PROG_LEN_STEP, 1, pre ? F_MASK : 0, sa, pre ? sa - s->batch : nullptr))) return rc;
+                } else if ((rc = launch_exchanged(s, PROG_LEN_STEP, 1, pre ? F_MASK : 0, sa, pre ? sa - s->batch : nullptr, pre != 0))) return rc;
                 return fuse_next ? ION_OK : launch_exchanged(s, PROG_ROT, 0, F_MASK, sa, nullptr);
             }
             if (fast_l_path(s)) {
@@ -1805,13 +1854,16 @@ struct PeerBlob {  // what a shard tells its neighbours (ION_PEER_BLOB_BYTES)
 };
 static_assert(sizeof(PeerBlob) == 96, "PeerBlob layout");
 
-size_t halo_block_words(const ion_sim *s) { return (size_t)ion::HF_COUNT + 2 * 2 * (size_t)s->Rp * 2; }  // cplx = 2 words
+// flags, staging[2 sides][2 slots][Rp] of the exchange kernel, fstage[2 sides][2 slots][Rp] of the fused exchange (cplx = 2 words)
+size_t halo_block_words(const ion_sim *s) { return (size_t)ion::HF_COUNT + 2 * (2 * 2 * (size_t)s->Rp * 2); }
 
 int ensure_halo_flags(ion_sim *s)
 {
     if (s->hflags) return ION_OK;
     if (int rc = dev_alloc(&s->hflags, halo_block_words(s))) return rc;
     CUDA_TRY(cudaMemset(s->hflags, 0, halo_block_words(s) * sizeof(unsigned long long)));
+    if (int rc = dev_alloc(&s->hf_sent, 2 * (size_t)s->S)) return rc;
+    CUDA_TRY(cudaMemset(s->hf_sent, 0, 2 * (size_t)s->S * sizeof(unsigned long long)));
     return ION_OK;
 }
 }  // namespace
@@ -1874,6 +1926,7 @@ int ion_sim_attach_peer(ion_sim_t *s, int side, const void *blob, int64_t blob_b
     const int facing = 1 - side;  // the neighbour's side that faces me
     s->peer_flags[side] = pblock;
     s->peer_stage[side] = reinterpret_cast<cplx *>(pblock + ion::HF_COUNT) + (size_t)facing * 2 * s->Rp;
+    s->peer_fstage[side] = reinterpret_cast<cplx *>(pblock + ion::HF_COUNT) + (size_t)(4 + facing * 2) * s->Rp;
     s->peers_attached = (!s->g_lo || s->peer_flags[0]) && (!s->g_hi || s->peer_flags[1]);
     if (s->len_fold_state == -1) s->len_fold_state = 0;  // the folded length-gauge step of a shard needs the engine's own exchange: decide again
     s->invalidate_graphs();

@@ -12,7 +12,7 @@ TOL = 1e-10
 def _run_sharded(p, world, n_steps=None, what=0, cut_parity=None):
     from ionization_b200 import parallel
 
-    shards = [parallel.ShardedSimulation(p, r, world, device=0, use_torch_stream=False, cut_parity=cut_parity) for r in range(world)]
+    shards = [parallel.ShardedSimulation(p, r, world, device=devices[r] if devices else 0, use_torch_stream=False, cut_parity=cut_parity) for r in range(world)]
     ex = parallel.LocalExchanger(shards)
     taus, fields = p["taus"][:n_steps], p["fields"][:n_steps]
     import torch
@@ -153,7 +153,7 @@ def test_segmented_line_split_operator_long_mesh():
         assert rel_err(g, ref) < TOL, kind
 
 
-def _run_sharded_device(p, world, n_steps=None, what=0, cut_parity=None):
+def _run_sharded_device(p, world, n_steps=None, what=0, cut_parity=None, devices=None):
     """the production transport: shards linked with ion_sim_attach_peer, advanced by the device-resident loop with the
     engine's own halo-exchange kernel (flags + stores into the neighbour's ghost channel).  Several shards in ONE process
     on one GPU: every shard is driven from its own host thread, as every rank would be from its own process."""
@@ -161,7 +161,7 @@ def _run_sharded_device(p, world, n_steps=None, what=0, cut_parity=None):
 
     from ionization_b200 import parallel
 
-    shards = [parallel.ShardedSimulation(p, r, world, device=0, use_torch_stream=False, cut_parity=cut_parity) for r in range(world)]
+    shards = [parallel.ShardedSimulation(p, r, world, device=devices[r] if devices else 0, use_torch_stream=False, cut_parity=cut_parity) for r in range(world)]
     parallel.ShardedSimulation.attach_local(shards)
     taus, fields = p["taus"][:n_steps], p["fields"][:n_steps]
     for s in shards:
@@ -223,6 +223,32 @@ def test_peer_memory_halo_exchange_equals_unsharded_run_on_a_larger_mesh(kind):
         g_ref = sim.read_g()[0]
     g, _ = _run_sharded_device(p, 4)
     assert rel_err(g, g_ref) < 1e-12
+
+
+@pytest.mark.parametrize("shape", [(600, 64, 70), (600, 64, 150), (3000, 16, 70), (5000, 16, 70)])
+def test_halo_exchange_fused_into_the_length_gauge_step_equals_unsharded_run(shape):
+    """PROG_LEN_STEP_HALO: the boundary CTAs of the folded step store their channel into the neighbour's memory and read their ghost
+    partner from the slot the neighbour's previous launch filled -- no exchange kernel between fused steps.  The default for shards
+    whose neighbours live on OTHER GPUs (a CTA that spins for a neighbour's kernel must not share a device with it), so this test
+    needs two GPUs: one shard per device, graph chunks of 64 steps, r-segments included."""
+    import torch
+
+    from ionization_b200 import configs, engine
+    from ionization_b200 import units as u
+
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs two GPUs (one l-block shard per device)")
+    world = min(n_dev, 4)
+    R, L, n = shape
+    p = configs.spherical_harmonic_problem(r_bound=0.1 * R * u.bohr_radius, r_points=R, l_bound=L, gauge="LEN", n_steps=n,
+                                           pulse=configs.sinc_pulse(20 * u.asec, 5 * u.Jcm2), time_initial=-n / 2 * u.asec, time_final=n / 2 * u.asec)
+    for steps in (n, 1):  # a single step: the stand-alone exchange only
+        with engine.DeviceSimulation.from_problem(p) as sim:
+            sim.step(p["taus"][:steps], p["fields"][:steps])
+            g_ref = sim.read_g()[0]
+        g, _ = _run_sharded_device(p, world, n_steps=steps, devices=list(range(world)))
+        assert rel_err(g, g_ref) < 1e-12
 
 
 @pytest.mark.parametrize("kind", ["LEN", "VEL"])
