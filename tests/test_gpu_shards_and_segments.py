@@ -12,7 +12,7 @@ TOL = 1e-10
 def _run_sharded(p, world, n_steps=None, what=0, cut_parity=None):
     from ionization_b200 import parallel
 
-    shards = [parallel.ShardedSimulation(p, r, world, device=devices[r] if devices else 0, use_torch_stream=False, cut_parity=cut_parity) for r in range(world)]
+    shards = [parallel.ShardedSimulation(p, r, world, device=0, use_torch_stream=False, cut_parity=cut_parity) for r in range(world)]
     ex = parallel.LocalExchanger(shards)
     taus, fields = p["taus"][:n_steps], p["fields"][:n_steps]
     import torch
