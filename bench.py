@@ -474,9 +474,11 @@ def extra_c5_sharded(rank, world, local_rank, n_t=100):
     shard.close()
     out.update({"ms_per_step": ms, "updates_per_s": R * L / (ms * 1e-3), "hbm_roofline_frac_per_gpu": R * L / (ms * 1e-3) / world * BYTES_PER_UPDATE / (peak * 1e9),
                 "partitioning": f"{world} contiguous l-blocks of ~{L // world} channels cut at odd channels (every odd pair local), one ghost channel per neighbour = the read-only "
-                                "even-pair partner of the block's first / last pair; every shard runs the one-kernel folded step (PROG_LEN_STEP) of the unsharded engine",
+                                "even-pair partner of the block's first / last pair; every shard runs the one-kernel folded step of the unsharded engine",
                 "halo_bytes_per_exchange_per_neighbour": R * 16, "exchanges_per_step": (n_ex - n_ex0) / n_t, "exchanges_done": n_ex, "halo_aborted": bool(aborted),
-                "transport": "engine kernel over NVLink peer memory (CUDA IPC), inside the captured step loop; NCCL only for rendezvous and the scalar all-reduce",
+                "transport": "fused into the step kernel (PROG_LEN_STEP_HALO): the boundary CTAs store their channel into the neighbour's memory over NVLink (CUDA IPC peer memory) in the epilogue "
+                             "and read the ghost partner the neighbour's previous launch delivered in the prologue; the stand-alone exchange kernel (counted in exchanges_per_step) only "
+                             "before the first and after the last step of a call; NCCL only for rendezvous and the scalar all-reduce",
                 "norm": float(rec[0]), "gpu_launches_per_rank": int(launches)})
     if rank == 0:
         ms_same, g_ref = unsharded({})  # the shards run the same folded one-kernel step as the unsharded engine
