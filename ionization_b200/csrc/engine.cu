@@ -311,7 +311,10 @@ int launch_unit_prog(ion_sim *s, const ion::UnitParams &p, dim3 grid)
         auto kern = ion::k_unit<MM, PROG, TMAX, SEG>;                                                               \
         CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));                                                                \
     } while (0)
-    if (s->S > 1) ION_LAUNCH(4, 512, true);  // r-segments: T_seg + 2H <= 512 threads
+    if (s->S > 1 && s->M == 8) {  // long LineMesh channels (Crank-Nicolson program): eight rows per thread, 256-thread CTAs
+        if constexpr (PROG == ion::PROG_LINE_CN) ION_LAUNCH(8, 256, true);
+        else return fail(ION_ESTATE, "internal: eight rows per thread in r-segments is built for the LineMesh Crank-Nicolson program only");
+    } else if (s->S > 1) ION_LAUNCH(4, 512, true);  // r-segments: T_seg + 2H <= 512 threads
     else if (s->M == 8) ION_LAUNCH(8, 256, false);  // eight rows per thread, 256-thread CTAs (r_points <= 2048)
     else if (s->tmax == 256) ION_LAUNCH(4, 256, false);
     else if (s->tmax == 512) ION_LAUNCH(4, 512, false);
@@ -651,7 +654,7 @@ int ensure_factor(ion_sim *s, double tau)
                     if (std::getenv("ION_DEBUG")) std::fprintf(stderr, "[ion] r-segments: multipliers over 16 threads <= %.3g, halo %d threads\n", std::exp(mx16), H);
                 }
             }
-            if (reach == 0 || s->T_seg + 2 * H > 512)
+            if (reach == 0 || s->T_seg + 2 * H > (s->M == 8 ? 256 : 512))
                 return fail(ION_ENOTSUP,
                             "r_points > 4096 needs the Crank-Nicolson LU multipliers to decay below 1e-30 within the segment halo; this "
                             "time step is too large for the radial spacing (reduce time_step or increase the spacing)");
@@ -1496,22 +1499,30 @@ int ion_sim_create_sharded(int program, int64_t L_total, int64_t l_begin, int64_
     {
         if (env[0] == '8' && R <= 2048 && program != ION_SH_LEN_ADI) M = 8;              // experiment: 256 threads x 8 rows
     }
+    // Long LineMesh channels of the Crank-Nicolson program (r-segments): EIGHT rows per thread.  The scans are the expensive
+    // part -- the program rebuilds its pivots every step with a Kogge-Stone scan of 2x2 complex Moebius matrices -- and
+    // their cost per thread does not depend on the rows a thread holds; the 256-row halos shrink from 64 to 32 threads, and at 128
+    // registers two 256-thread CTAs share an SM.  configs[1] (1024 x 2^16): 1889 -> 1108 us per step (17.4 -> 29.6 % of the roofline).
+    if (program == ION_LINE_LEN_CN && R > 4096) {
+        const char *env = std::getenv("ION_LINE_M");
+        if (!(env && env[0] == '4')) M = 8;
+    }
     int64_t T = (R + M - 1) / M;
     T = (T + 31) / 32 * 32;
     int S = 1, T_seg = (int)T, H = 0;
-    if (T > 1024) {  // r-segments with halos (kernels.cuh); the halo width is fixed when the LU factors are built
+    if (T > (M == 8 ? 256 : 1024)) {  // r-segments with halos (kernels.cuh); the halo width is fixed when the LU factors are built
         // + 2 x 32 halo threads per unit of reach (2 x 64 with r-pair bricks): 448 or 512 threads per CTA.  The length-gauge
         // split-operator step (32-thread halos) takes 192-thread segments instead: 256-thread CTAs, two per SM at 128 registers,
         // whose load / solve / store phases overlap -- 33 % recomputed rows instead of 17 %, and still 7 % faster on the
         // HBM-resident 16384 x 4096 mesh (1274 -> 1180 us per step; 160: 1275, 256: 1548, 320: 1346)
         // With half-warp halos (ensure_factor: the multipliers decay below 1e-18 over 64 rows) the same 256-thread CTA holds 224
         // interior threads: 14 % recomputed rows.
-        T_seg = (program == ION_SH_LEN_SO) ? 224 : 384;
+        T_seg = (program == ION_SH_LEN_SO) ? 224 : (M == 8 ? 192 : 384);
         if (const char *env = std::getenv("ION_TSEG")) {  // A/B switch
             const int v = std::atoi(env);
             if (v >= 64 && v <= 384 && v % 32 == 0) T_seg = v;
         }
-        H = 64;
+        H = M == 8 ? 32 : 64;
         S = (int)((T + T_seg - 1) / T_seg);
         T = (int64_t)S * T_seg;
     }

@@ -713,8 +713,9 @@ template <int M, int PROG, int TMAX, bool SEG>
 #ifndef ION_PAIR_MINB
 #define ION_PAIR_MINB 1
 #endif
+// (eight rows per thread in r-segments -- long LineMesh channels, see engine.cu -- are capped at 128 registers: two 256-thread CTAs per SM)
 __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) && TMAX <= 512) ? (M <= 4 ? 1024 / TMAX : 2)
-                                                                                            : ((M <= 4 && TMAX <= 256) ? 2 : (TMAX == 512 && M == 4 ? ION_PAIR_MINB : 1)))
+                                                                                            : ((M <= 4 && TMAX <= 256) ? 2 : (TMAX == 512 && M == 4 ? ION_PAIR_MINB : ((M == 8 && SEG) ? 2 : 1))))
     k_unit(const UnitParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
