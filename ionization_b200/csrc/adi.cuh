@@ -24,6 +24,7 @@
 // PW = 8 positions are one full 128-byte line per channel; L <= 8 * 512 channels.
 #pragma once
 #include "common.cuh"
+#include "kernels.cuh"  // e_of
 
 namespace ion {
 
@@ -257,6 +258,98 @@ __global__ void __launch_bounds__(ADI_MAX_THREADS, 1) k_adi_l(const AdiParams p)
         x = fma_mi(eb[k], x, c_scale(y[k], w[k]));
         const int l = l0 + k;
         if (l < L) p.out[((size_t)b * L + l) * Rp + pos] = c_make(fma(2.0, x.x, -g1[k].x), fma(2.0, x.y, -g1[k].y));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The closing radial pass of an ADI step: x = (1 + i tau H0)^-1 g [* mask] on every channel, out of place.
+// k_unit<PROG_CN> gives a channel to one CTA of T threads x 4 rows (500 CTAs of 512 threads on 148 SMs at 2000 x 500: 3.4 waves,
+// one CTA per SM).  Here a thread holds EIGHT consecutive rows -- in the M = 4 layout rows 8p .. 8p+7 are the elements [k][2p],
+// [k][2p+1], k = 0..3, i.e. 32 contiguous bytes per k, so every access is still fully coalesced and nothing is transposed --
+// and the LU factors go straight into registers (each thread needs exactly its own rows').  The two affine scans cost the same
+// per thread whatever the rows it holds, so their cost per point halves; T/2 <= 256 threads at <= 128 registers: two CTAs per SM.
+// Solve only (no 2x - g), so u = w y overwrites g.  Recurrences as cn_channel / cn8 (kernels.cuh).
+// grid = (channels, batch), block = T/2 rounded up to whole warps.
+// ---------------------------------------------------------------------------------------------
+struct AdiRParams {
+    const cplx *psi;         // [batch][L][4][T]
+    cplx *out;               // [batch][L][4][T]
+    const cplx *w;           // [L][4][T]  1 / pivot
+    const cplx *aggP;        // [L][T]     4-row chunk multipliers, forward
+    const cplx *aggQ;        // [L][T]     backward
+    const double *toff;      // [4][T]     tau * h_off[i]
+    const double *toff_prev; // [T]        tau * h_off[4 t - 1]
+    const double *mask;      // [4][T] or nullptr
+    int L, T, short_scan;
+};
+
+__global__ void __launch_bounds__(256, 2) k_adi_r(const AdiRParams p)
+{
+    __shared__ __align__(16) cplx sm[128];
+    const int tid = threadIdx.x, NT = blockDim.x, T = p.T;
+    const int l = blockIdx.x, b = blockIdx.y;
+    const bool ok = 2 * tid < T;  // T is even (a multiple of 32)
+    const int c0 = 2 * tid;       // first column of the thread: rows 8 tid + 4 j + k at [k][c0 + j]
+    pdl_launch_dependents();
+    // ---- everything that does not depend on psi ----
+    const cplx *wch = p.w + (size_t)l * 4 * T;
+    cplx w[8];
+    double to[8];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            w[4 * j + k] = ok ? ld_c(wch + k * T + c0 + j) : c_make(1.0, 0.0);
+            to[4 * j + k] = ok ? p.toff[k * T + c0 + j] : 0.0;
+        }
+    }
+    const double to_prev = ok ? p.toff_prev[c0] : 0.0;
+    const cplx wprev = (ok && tid > 0) ? ld_c(wch + 3 * T + c0 - 1) : c_zero();
+    cplx Pt = c_zero(), Qt = c_zero();
+    if (ok) {
+        Pt = c_mul(ld_c(p.aggP + (size_t)l * T + c0), ld_c(p.aggP + (size_t)l * T + c0 + 1));
+        Qt = c_mul(ld_c(p.aggQ + (size_t)l * T + c0), ld_c(p.aggQ + (size_t)l * T + c0 + 1));
+    }
+    pdl_wait();
+    const cplx *src = p.psi + ((size_t)b * p.L + l) * 4 * T;
+    cplx g[8];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) g[4 * j + k] = ok ? ld_c(src + k * T + c0 + j) : c_zero();
+    }
+    // forward, zero inflow
+    cplx z = g[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) z = c_fma(e_of(to[k - 1], w[k - 1]), z, g[k]);
+    const cplx yin = affine_scan_block_exclusive<true>(Pt, z, sm, sm + 32, tid, NT, p.short_scan);
+    // forward, true inflow; u = w y overwrites g
+    cplx y = c_fma(e_of(to_prev, wprev), yin, g[0]);
+    g[0] = c_mul(w[0], y);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+        y = c_fma(e_of(to[k - 1], w[k - 1]), y, g[k]);
+        g[k] = c_mul(w[k], y);
+    }
+    // backward, zero inflow
+    z = g[7];
+#pragma unroll
+    for (int k = 6; k >= 0; --k) z = c_fma(e_of(to[k], w[k]), z, g[k]);
+    double mk[8];  // loaded late: the registers are needed above (the loads are issued before the scan's barrier)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mk[4 * j + k] = (ok && p.mask) ? p.mask[k * T + c0 + j] : 1.0;
+    }
+    const cplx xin = affine_scan_block_exclusive<false>(Qt, z, sm + 64, sm + 96, tid, NT, p.short_scan);
+    // backward, true inflow; mask; store
+    cplx *dst = p.out + ((size_t)b * p.L + l) * 4 * T;
+    cplx x = c_fma(e_of(to[7], w[7]), xin, g[7]);
+    if (ok) st_c(dst + 3 * T + c0 + 1, c_scale(x, mk[7]));
+#pragma unroll
+    for (int k = 6; k >= 0; --k) {
+        x = c_fma(e_of(to[k], w[k]), x, g[k]);
+        if (ok) st_c(dst + (k & 3) * T + c0 + (k >> 2), c_scale(x, mk[k]));
     }
 }
 

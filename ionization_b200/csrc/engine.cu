@@ -897,6 +897,49 @@ int launch_adi_l(ion_sim *s, const double *sa)
     return ION_OK;
 }
 
+// the closing radial solve of an ADI step with eight rows per thread (adi.cuh: k_adi_r): channels of at most 2048 points in the
+// M = 4 layout, one CTA of T/2 threads per channel; everything else keeps k_unit<PROG_CN>
+bool adi_r_ok(const ion_sim *s)
+{
+    const char *env = std::getenv("ION_NO_ADI_R");
+    return !(env && env[0] == '1') && s->M == 4 && s->S == 1 && s->T <= 512 && s->T >= 64;
+}
+
+int launch_adi_r(ion_sim *s)
+{
+    if (!s->psi2) return fail(ION_ESTATE, "internal: ADI buffers missing");
+    ion::AdiRParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.psi = s->psi;
+    p.out = s->psi2;
+    p.w = s->w;
+    p.aggP = s->aggP;
+    p.aggQ = s->aggQ;
+    p.toff = s->toff;
+    p.toff_prev = s->toff_prev;
+    p.mask = s->mask;
+    p.L = s->L;
+    p.T = s->T;
+    p.short_scan = s->short_scan;
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(s->L, s->batch);
+    cfg.blockDim = dim3((s->T / 2 + 31) / 32 * 32);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = s->use_pdl ? 1 : 0;
+    prof_begin(s, KK_CN);
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_adi_r, p));
+    prof_end(s);
+    s->launch_count++;
+    std::swap(s->psi, s->psi2);
+    return ION_OK;
+}
+
 // bring the current state back into the buffer the rest of the API (and every captured graph) starts from
 int restore_home(ion_sim *s)
 {
@@ -1055,6 +1098,7 @@ int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, int pre, b
         case ION_SH_LEN_ADI:
             // (1 - i tau H0)_r, (1 + i tau Hint)^-1_l, (1 - i tau Hint)_l | (1 + i tau H0)^-1_r, mask   (evolution_methods.py:49-77)
             if ((rc = launch_adi_l(s, sa))) return rc;
+            if (adi_r_ok(s)) return launch_adi_r(s);
             return launch_unit(s, PROG_CN, 0, F_MASK | F_SOLVE_ONLY, nullptr, nullptr);
         case ION_LINE_LEN_SO: return launch_unit(s, PROG_LINE_SO_LEN, 0, F_MASK, sa, nullptr);
         case ION_LINE_VEL_SO: return launch_unit(s, PROG_LINE_SO_VEL, 0, F_MASK, sa, nullptr);
