@@ -10,7 +10,7 @@ import sys
 
 workload, rep = sys.argv[1], sys.argv[2]
 out_path = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
-PROGS = {"0": "rot", "1": "rot_cn_rot", "2": "h2", "3": "h2_cn_h2", "4": "cn", "5": "line_so_len", "6": "line_so_vel", "7": "line_cn", "8": "len_step"}
+PROGS = {"0": "rot", "1": "rot_cn_rot", "2": "h2", "3": "h2_cn_h2", "4": "cn", "5": "line_so_len", "6": "line_so_vel", "7": "line_cn", "8": "len_step", "9": "len_step_obs", "10": "len_step_halo"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
