@@ -567,3 +567,27 @@ def test_tiny_and_ragged_line_meshes_against_oracle(kind, Z):
     ref = restate.run_line(p, store_every_step=False)
     assert rel_err(g, ref["g"]) < TOL
     assert abs(norm - ref["norm"][-1]) < TOL * max(1.0, ref["norm"][-1])
+
+
+def test_adi_radial_solve_with_eight_rows_per_thread_equals_the_unit_kernel(monkeypatch):
+    """k_adi_r (adi.cuh: eight consecutive rows per thread, LU factors in registers) against k_unit<PROG_CN> (ION_NO_ADI_R=1) and the oracle,
+    on a ragged mesh with a mask"""
+    from ionization_b200 import configs, units as u
+    from oracle import restate
+
+    eng = _engine()
+    L, R = 12, 1777
+    p = configs.spherical_harmonic_problem(r_bound=0.1 * R * u.bohr_radius, r_points=R, l_bound=L, gauge="LEN", n_steps=10)
+    p["kind"] = "sh_len_adi"
+    p["mask"] = np.cos(np.linspace(0, 1.1, R)) ** 0.125
+    p["fields"] = np.asarray(p["fields"]) * 30.0 + 1e10
+    ref = restate.run_sh(p, store_every_step=False)
+    out = {}
+    for env in ("0", "1"):
+        monkeypatch.setenv("ION_NO_ADI_R", env)
+        with eng.DeviceSimulation.from_problem(p, with_states=False) as sim:
+            sim.step(p["taus"], p["fields"])
+            out[env] = sim.read_g()[0]
+        assert rel_err(out[env], ref["g"]) < TOL, env
+    monkeypatch.delenv("ION_NO_ADI_R")
+    assert rel_err(out["0"], out["1"]) < 1e-13

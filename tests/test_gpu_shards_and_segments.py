@@ -306,3 +306,62 @@ def test_segmented_line_crank_nicolson_ensemble_spans_several_waves():
             sim.step(p["taus"][:n], np.ascontiguousarray(fields[:, b]))
             g1 = sim.read_g()[0, 0]
         assert rel_err(g[b], g1) < 1e-13
+
+
+def test_line_crank_nicolson_eight_rows_per_thread_equals_four_rows_per_thread(monkeypatch):
+    """Long LineMesh channels of the Crank-Nicolson program take eight rows per thread (layout with M = 8, 256-thread segment CTAs,
+    32-thread halos); ION_LINE_M=4 keeps the four-row kernels.  Same inputs, both against each other and against the oracle."""
+    from ionization_b200 import engine
+    from oracle import cport
+
+    base = dict(load_golden("line_len_cn_1024"))
+    Z = 2 ** 13 + 37  # ragged: the last segment is partly padding
+    z = np.linspace(-1, 1, Z) * base["z"][-1] * 8
+    dz = z[1] - z[0]
+    scale = (float(base["delta_z"]) / dz) ** 2
+    p = dict(base)
+    p.update(Z=Z, z=z, delta_z=dz, h_off=np.full(Z - 1, base["h_off"][0] * scale), w_z=z * (base["w_z"][-1] / base["z"][-1]), mask=np.cos(np.linspace(0, 1.0, Z)) ** 0.125)
+    p["h_diag"] = np.full(Z, -2 * p["h_off"][0]) + 0j + np.interp(z, base["z"], np.real(base["h_diag"]) + 2 * base["h_off"][0])
+    rng = np.random.default_rng(11)
+    g0 = (rng.standard_normal(Z) + 1j * rng.standard_normal(Z)) * np.exp(-((z / z[-1]) ** 2) * 2)
+    p["g0"] = g0 / np.sqrt(np.sum(np.abs(g0) ** 2) * dz)
+    p["state_rows"] = p["g0"][None, :]
+    n = 10
+    p["taus"], p["fields"] = p["taus"][:n], 0.05 * np.asarray(p["fields"][:n])
+    ref = cport.line_steps(p)
+    out = {}
+    for m in ("8", "4"):
+        monkeypatch.setenv("ION_LINE_M", m)
+        with engine.DeviceSimulation.from_problem(p) as sim:
+            sim.step(p["taus"], p["fields"])
+            out[m] = sim.read_g()[0, 0]
+            norm = sim.observe(engine.nat.OBS_NORM)[0, 0]
+        assert rel_err(out[m], ref) < TOL, m
+        assert abs(norm - np.sum(np.abs(ref) ** 2) * dz) < TOL
+    monkeypatch.delenv("ION_LINE_M")
+    assert rel_err(out["8"], out["4"]) < 1e-12
+
+
+def test_half_warp_halos_equal_full_warp_halos(monkeypatch):
+    """Length-gauge r-segments recompute 16 halo threads (64 rows) per side when the host finds the LU multipliers below 1e-18 over any
+    aligned 64 rows; ION_HALO16=0 keeps the 32-thread halos.  Same mesh, both ways, against each other and the oracle."""
+    from ionization_b200 import configs, engine
+    from ionization_b200 import units as u
+    from oracle import cport
+
+    R, L, n = 6000, 10, 16
+    p = configs.spherical_harmonic_problem(r_bound=0.1 * R * u.bohr_radius, r_points=R, l_bound=L, gauge="LEN", n_steps=n,
+                                           pulse=configs.sinc_pulse(20 * u.asec, 20 * u.Jcm2), time_initial=-n / 2 * u.asec, time_final=n / 2 * u.asec)
+    rng = np.random.default_rng(4)
+    g0 = (rng.standard_normal((L, R)) + 1j * rng.standard_normal((L, R))) * np.exp(-((p["r"] / p["r"][-1]) ** 2) * 3)[None, :]
+    p["g0"] = g0 / np.sqrt(np.sum(np.abs(g0) ** 2) * float(p["delta_r"]))
+    ref = cport.sh_steps(p)
+    out = {}
+    for h in ("1", "0"):
+        monkeypatch.setenv("ION_HALO16", h)
+        with engine.DeviceSimulation.from_problem(p) as sim:
+            sim.step(p["taus"], p["fields"])
+            out[h] = sim.read_g()[0]
+        assert rel_err(out[h], ref) < TOL, h
+    monkeypatch.delenv("ION_HALO16")
+    assert rel_err(out["1"], out["0"]) < 1e-13
