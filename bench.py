@@ -168,6 +168,10 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+PORT_NOTE = ("the reference package itself (numpy / scipy.sparse / one Cython tdma, single core; it cannot travel to the GPU box) measured 0.93 M updates/s on "
+             "configs[2] and 2.3 M updates/s on configs[0] in the build container (BASELINE.md section 2): this C/OpenMP restatement is ~76x faster than the package")
+
+
 def cpu_steps(problem, n, members=1):
     """n time steps of the workload on the CPU port; returns grid-point updates done"""
     from oracle import cport
@@ -525,7 +529,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "grid-point updates/s (SphericalHarmonicMesh CN+split)", "value": value, "unit": "updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "complex128 (f64)", "data": "synthetic", "config": {"workload": desc, "mesh_points": L * R, "time_steps_per_step": n_t},
-        "cpu_baseline": {"value": value, "unit": "updates/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "updates/s", "cores": cores, "kind": "port", "sample": sample, "note": PORT_NOTE},
         "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -724,7 +728,7 @@ def main():
         try:
             v, n_cpu, dt_cpu, cores = cpu_reference_rate(problem, seconds_target=12.0)
             cpu_baseline = {"value": v, "unit": "updates/s", "cores": cores, "kind": "port",
-                            "sample": f"first {n_cpu} of {len(problem['taus'])} time steps of the same mesh ({dt_cpu:.1f} s); oracle C restatement, OpenMP"}
+                            "sample": f"first {n_cpu} of {len(problem['taus'])} time steps of the same mesh ({dt_cpu:.1f} s); oracle C restatement, OpenMP", "note": PORT_NOTE}
         except Exception as exc:  # the checker is optional at bench time
             cpu_baseline = {"value": None, "unit": "updates/s", "cores": 0, "kind": "port", "sample": f"unavailable: {exc}"}
 
