@@ -144,6 +144,9 @@ struct ion_sim {
     cplx *state_rows = nullptr;
     int *state_first = nullptr, *state_order = nullptr;
     double *partial = nullptr, *ip_out = nullptr, *obs_out = nullptr;
+    // length gauge, fused observation: second set of the two buffers above -- the record of step n is assembled on the side branch while
+    // the kernel of step n + 1 already fills the other set (obs_parity, ev_done as for the slab kernel)
+    double *partial2 = nullptr, *ip_out2 = nullptr;
     double *slab_partial = nullptr, *slab_ip = nullptr;  // per-slab partial sums of the fused observation (slab.cuh)
     unsigned *obs_counter = nullptr;                     // [batch] CTAs of k_slab_obs_assemble that are done
     // the record assembly of a fused observation runs on a side branch of the captured graph, so that the next step's kernels
@@ -198,6 +201,8 @@ struct ion_sim {
         if (psi2) cudaFree(psi2);
         if (slab_partial) cudaFree(slab_partial);
         if (slab_ip) cudaFree(slab_ip);
+        if (partial2) cudaFree(partial2);
+        if (ip_out2) cudaFree(ip_out2);
         if (obs_counter) cudaFree(obs_counter);
         if (ev_fork) cudaEventDestroy(ev_fork);
         for (auto e : ev_done)
@@ -1055,10 +1060,35 @@ int enqueue_step(ion_sim *s, const double *sa, const double *sb_next, int pre, b
             if (fast_l_path(s) && s->len_fold_state == 1) {
                 // the previous step's deferred tail (its scalar is the row before sa), the mask and this step's head ride along
                 if (prev.what && pre) {
-                    if ((rc = launch_unit(s, PROG_LEN_STEP_OBS, 1, F_MASK, sa, sa - s->batch, prev.what))) return rc;
-                    prof_begin(s, KK_OBSERVE);
-                    rc = launch_observe_finish(s, prev.what, prev.dst);
-                    prof_end(s);
+                    // the record is assembled on a side branch (event fork / join, also inside the captured graphs): the next step's kernel
+                    // depends on this step's kernel only; the partial-sum buffers alternate between two sets
+                    const bool on_side = s->side && s->partial2 && s->ip_out2 && !s->profiling;
+                    const int k = s->obs_parity;
+                    if (on_side) {
+                        if (s->side_pending[k]) {  // the assembly that last read this set (two observations ago) must be done
+                            CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_done[k], 0));
+                            s->side_pending[k] = false;
+                        }
+                        if (k) std::swap(s->partial, s->partial2), std::swap(s->ip_out, s->ip_out2);
+                    }
+                    rc = launch_unit(s, PROG_LEN_STEP_OBS, 1, F_MASK, sa, sa - s->batch, prev.what);
+                    if (rc == ION_OK && on_side) {
+                        cudaStream_t main_stream = s->stream;
+                        if (cudaEventRecord(s->ev_fork, main_stream) != cudaSuccess || cudaStreamWaitEvent(s->side, s->ev_fork, 0) != cudaSuccess)
+                            rc = fail(ION_ECUDA, "fork of the observation branch failed");
+                        if (rc == ION_OK) {
+                            s->stream = s->side;
+                            rc = launch_observe_finish(s, prev.what, prev.dst);
+                            s->stream = main_stream;
+                        }
+                        if (rc == ION_OK && cudaEventRecord(s->ev_done[k], s->side) != cudaSuccess) rc = fail(ION_ECUDA, "cudaEventRecord failed");
+                        if (rc == ION_OK) s->side_pending[k] = true, s->obs_parity ^= 1;
+                    } else if (rc == ION_OK) {
+                        prof_begin(s, KK_OBSERVE);
+                        rc = launch_observe_finish(s, prev.what, prev.dst);
+                        prof_end(s);
+                    }
+                    if (on_side && k) std::swap(s->partial, s->partial2), std::swap(s->ip_out, s->ip_out2);
                     if (rc) return rc;
                 } else if ((rc = launch_exchanged(s, PROG_LEN_STEP, 1, pre ? F_MASK : 0, sa, pre ? sa - s->batch : nullptr, pre != 0))) return rc;
                 return fuse_next ? ION_OK : launch_exchanged(s, PROG_ROT, 0, F_MASK, sa, nullptr);
@@ -1338,6 +1368,20 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
     if (int rc = len_fold_prepare(s)) return rc;
     if (s->S > 1 || s->program == ION_SH_LEN_ADI)
         if (int rc = ensure_second_buffer(s)) return rc;  // segmented kernels run out of place
+    if (n_obs && s->len_fold_state == 1 && s->S == 1 && s->L_own == s->L_total) {  // length gauge: the record assembly runs on a side branch
+        if (!s->partial2)
+            if (int rc = dev_alloc(&s->partial2, (size_t)s->batch * s->L_own * (4 + ION_MAX_RADII))) return rc;
+        if (!s->ip_out2) {
+            const size_t n = (size_t)s->batch * std::max(s->n_states, 1) * 2;
+            if (int rc = dev_alloc(&s->ip_out2, n)) return rc;
+            CUDA_TRY(cudaMemsetAsync(s->ip_out2, 0, n * sizeof(double), s->stream));
+        }
+        if (!s->side) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+            for (auto &e : s->ev_done) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+    }
     if (n_obs && s->slab_state == 1) {  // per-slab partial sums of the fused observation (slab.cuh)
         s->slab_partial_half = (size_t)s->batch * s->slab_slabs * s->L * (4 + ION_MAX_RADII);
         s->slab_ip_half = (size_t)s->batch * s->slab_slabs * std::max(s->n_states, 1) * 2;
@@ -1747,6 +1791,10 @@ int ion_sim_set_observables(ion_sim_t *s, double ipm, const double *r_j, int64_t
     if (s->ip_out) {
         cudaFree(s->ip_out);
         s->ip_out = nullptr;
+    }
+    if (s->ip_out2) {
+        cudaFree(s->ip_out2);
+        s->ip_out2 = nullptr;
     }
     if (s->slab_ip) {
         cudaFree(s->slab_ip);
