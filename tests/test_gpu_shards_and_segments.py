@@ -308,15 +308,15 @@ def test_segmented_line_crank_nicolson_ensemble_spans_several_waves():
         assert rel_err(g[b], g1) < 1e-13
 
 
-def test_line_crank_nicolson_eight_rows_per_thread_equals_four_rows_per_thread(monkeypatch):
+@pytest.mark.parametrize("Z", [4097, 2 ** 13 + 37])
+def test_line_crank_nicolson_eight_rows_per_thread_equals_four_rows_per_thread(Z, monkeypatch):
     """Long LineMesh channels of the Crank-Nicolson program take eight rows per thread (layout with M = 8, 256-thread segment CTAs,
     32-thread halos); ION_LINE_M=4 keeps the four-row kernels.  Same inputs, both against each other and against the oracle."""
     from ionization_b200 import engine
     from oracle import cport
 
     base = dict(load_golden("line_len_cn_1024"))
-    Z = 2 ** 13 + 37  # ragged: the last segment is partly padding
-    z = np.linspace(-1, 1, Z) * base["z"][-1] * 8
+    z = np.linspace(-1, 1, Z) * base["z"][-1] * (Z / 1024)  # ragged sizes: the last segment is partly padding
     dz = z[1] - z[0]
     scale = (float(base["delta_z"]) / dz) ** 2
     p = dict(base)
