@@ -193,3 +193,29 @@ def test_fused_observation_equals_separate_observation(name, monkeypatch):
     assert rel_err(out["fused"][1], p["g_final"]) < TOL if n == len(p["taus"]) else True
     # the observed steps stayed on the fused schedule: far fewer launches than the single-sweep schedule needs
     assert out["fused"][2] < out["separate"][2]
+
+
+def test_full_pulse_parity_of_a_scan_member():
+    """BASELINE.json north_star: wavefunction, norm and ionization fraction <= 1e-10 relative AFTER THE FULL PULSE.  One member of configs[3]
+    (1000 x 200, length gauge), all 2000 time steps from the hydrogen ground state, on the timed schedule (CUDA graphs, folded step) against
+    the oracle C port (tools/full_pulse_parity.py runs the same check for the C3 shapes: profiles/r02g_full_pulse_parity.log)."""
+    from ionization_b200 import configs, engine
+    from oracle import cport
+
+    p = dict(configs.config4_member("LEN"))
+    with engine.DeviceSimulation.from_problem(p) as sim:
+        sim.step(p["taus"], p["fields"])
+        g = sim.read_g()[0]
+    ref = cport.sh_steps(p)
+    dr = float(p["delta_r"])
+    assert rel_err(g, ref) < TOL
+    norm, norm_ref = np.sum(np.abs(g) ** 2) * dr, np.sum(np.abs(ref) ** 2) * dr
+    assert abs(norm - norm_ref) < TOL * norm_ref
+
+    def ionization_fraction(x):
+        rows, ls = np.asarray(p["state_rows"]), np.asarray(p["state_l"])
+        bound = np.asarray(p["state_bound"], dtype=bool)
+        ips = np.array([np.sum(np.conj(rows[k]) * x[ls[k]]) * dr for k in range(len(ls))])
+        return 1.0 - np.sum(np.abs(ips[bound]) ** 2)
+
+    assert abs(ionization_fraction(g) - ionization_fraction(ref)) < TOL * abs(ionization_fraction(ref))
