@@ -162,6 +162,38 @@ ION_DEVINL void cp_async16(void *smem_dst, const void *gmem_src)
 ION_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 ION_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// Bulk asynchronous copies (the TMA engine's 1-D form, cp.async.bulk) signalling an mbarrier: one thread moves a whole contiguous
+// block global -> shared; the consumers wait on the barrier's phase.  Used by the ensemble kernel's psi prefetch (ensemble.cuh).
+ION_DEVINL unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+ION_DEVINL void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+ION_DEVINL void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+ION_DEVINL void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+ION_DEVINL void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    const unsigned a = smem_u32(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "ION_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n"
+        "@q bra ION_MBAR_DONE;\n"
+        "bra ION_MBAR_WAIT;\n"
+        "ION_MBAR_DONE:\n"
+        "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+
 // 128-bit global accesses of one complex128
 ION_DEVINL cplx ld_c(const cplx *p) { return *p; }
 ION_DEVINL void st_c(cplx *p, cplx v) { *p = v; }

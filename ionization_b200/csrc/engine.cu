@@ -706,9 +706,10 @@ int len_fold_prepare(ion_sim *s)
         const long long tasks = (long long)s->batch * (s->L / 2 - 1);
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
-        CUDA_TRY(cudaFuncSetAttribute(ion::k_len_ens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ion::ens_smem_bytes(ion::ENS_T)));
+        CUDA_TRY(cudaFuncSetAttribute(ion::k_len_ens<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ion::ens_smem_bytes(ion::ENS_T)));
+        CUDA_TRY(cudaFuncSetAttribute(ion::k_len_ens<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ion::ens_smem_bytes(ion::ENS_T)));
         int per_sm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ion::k_len_ens, ion::ENS_T, ion::ens_smem_bytes(ion::ENS_T)));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ion::k_len_ens<false>, ion::ENS_T, ion::ens_smem_bytes(ion::ENS_T)));
         if (per_sm >= 1 && tasks >= 4LL * per_sm * prop.multiProcessorCount) {
             s->ens_ctas = per_sm * prop.multiProcessorCount;
             s->ens_state = 1;
@@ -734,7 +735,13 @@ int launch_len_ens(ion_sim *s, const ion::UnitParams &p)
     cfg.attrs = attr;
     cfg.numAttrs = s->use_pdl ? 1 : 0;
     prof_begin(s, KK_LEN_ENS);
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_len_ens, p, n_pairs, s->batch));
+    {
+        // psi prefetch by the TMA engine (cp.async.bulk + mbarrier): 1095 -> 998 us per step on configs[3] (45.7 -> 50.1 % of the roofline);
+        // ION_ENS_BULK=0 keeps the 16 cp.async per thread for A/B timing
+        const char *env = std::getenv("ION_ENS_BULK");
+        if (env && env[0] == '0') CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_len_ens<false>, p, n_pairs, s->batch));
+        else CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_len_ens<true>, p, n_pairs, s->batch));
+    }
     prof_end(s);
     s->launch_count++;
     ion::UnitParams q = p;  // l = 0 and l = L - 1: units 0 and L/2 of the odd sweep

@@ -5,9 +5,10 @@
 // CTAs whose DRAM latency is exposed in every one of them (ncu: 32 % long-scoreboard stalls, two 256-thread CTAs per SM).
 // Here 2 CTAs per SM stay resident and walk over the (member, pair) tasks MEMBER-MAJOR with a grid stride -- neighbouring
 // pairs of the same member are in flight at the same time on other SMs, so the read-only partner channels still hit L2 -- and
-//   * the psi of the NEXT task (4 channels x 4 rows per thread = 64 KB per CTA at T = 256) is prefetched with cp.async into
-//     shared memory while the current task computes; every thread stages exactly the 16 values it will read itself, so the
-//     hand-over needs no barrier, only cp.async.wait_group;
+//   * the psi of the NEXT task (4 channels x 4 rows per thread = 64 KB per CTA at T = 256) is prefetched into shared memory while
+//     the current task computes -- by the TMA engine (BULK: four consecutive channels are ONE contiguous 64 KB block of the
+//     row-interleaved layout; cp.async.bulk issued by one thread behind the forward scan's barrier, completion on an mbarrier), or,
+//     for A/B timing, with 16 cp.async per thread (every thread stages exactly the values it will read itself);
 //   * the LU factors of the current pair are staged with cp.async at the top of the task and arrive under the trigonometry;
 //   * tau * h_off of the rows (the same for every pair) is staged once per CTA.
 // The arithmetic is the layout-2 path of k_unit<PROG_LEN_STEP>, instruction for instruction (same helpers): results are identical.
@@ -22,7 +23,7 @@ constexpr int ENS_T = 256;  // threads per CTA = threads per channel: r_points i
                             // than one CTA per task (profiles/r01c_whatif_experiments.md), so the kernel is used for T = 256 only.
 
 // dynamic shared memory: scan scratch 256 cplx | LU factors 8*T cplx | psi stage 16*T cplx | tau*off 9*(T/2) doubles
-inline size_t ens_smem_bytes(int T) { return (256 + 8 * (size_t)T + 16 * (size_t)T) * sizeof(cplx) + 9 * (size_t)(T / 2) * sizeof(double); }
+inline size_t ens_smem_bytes(int T) { return (256 + 8 * (size_t)T + 16 * (size_t)T) * sizeof(cplx) + 9 * (size_t)(T / 2) * sizeof(double) + 16; }
 
 // TASK ORDER.  An item is (block of ENS_MB consecutive members, channel pair); items are numbered block-major, pair-minor, and a
 // CTA takes the items blockIdx.x, blockIdx.x + gridDim.x, ... and walks through the members of an item one after the other.
@@ -31,6 +32,10 @@ inline size_t ens_smem_bytes(int T) { return (256 + 8 * (size_t)T + 16 * (size_t
 // pair's scan multipliers hit L1 for ENS_MB - 1 of every ENS_MB tasks (one third less L2 -> SM traffic, no factor wait).
 constexpr int ENS_MB = 16;
 
+// BULK: the psi of the next task -- four consecutive channels, i.e. ONE contiguous 64 KB block in the row-interleaved layout -- is moved
+// by the TMA engine (cp.async.bulk, four 16 KB copies issued by one thread, completion on an mbarrier) instead of 16 cp.async per thread;
+// the copy is issued behind the forward scan's barrier of the current task, when every thread has read the staging buffer.
+template <bool BULK>
 __global__ void __launch_bounds__(ENS_T, 2) k_len_ens(const UnitParams p, int n_pairs, int batch)
 {
     constexpr int M = 4, T = ENS_T;
@@ -39,6 +44,7 @@ __global__ void __launch_bounds__(ENS_T, 2) k_len_ens(const UnitParams p, int n_
     cplx *wsm = sm_scan + 256;                               // [8][T]
     cplx *stage = wsm + 8 * T;                               // [4 channels][4 rows][T]
     double *tosm = reinterpret_cast<double *>(stage + 16 * T);  // [9][T/2]
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tosm + 9 * (T / 2));  // BULK: psi of the next task has landed
 
     const int tl = threadIdx.x, pp = tl >> 1, TH = T >> 1;
     const bool odd = (tl & 1) != 0;
@@ -59,14 +65,28 @@ __global__ void __launch_bounds__(ENS_T, 2) k_len_ens(const UnitParams p, int n_
     auto prefetch_psi = [&](long long item, int mem) {
         const long long b = member_of(item, mem);
         const int l0 = 2 * (int)(item % n_pairs) + 1;
-        const cplx *src = p.psi + ((size_t)b * p.L + (l0 - 1)) * chan + tl;
+        if constexpr (BULK) {
+            if (tl == 0) {
+                const cplx *src = p.psi + ((size_t)b * p.L + (l0 - 1)) * chan;
+                mbar_expect_tx(mbar, (unsigned)(4 * chan * sizeof(cplx)));
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 4; ++c) bulk_g2s(stage + (size_t)c * chan, src + (size_t)c * chan, (unsigned)(chan * sizeof(cplx)), mbar);
+            }
+        } else {
+            const cplx *src = p.psi + ((size_t)b * p.L + (l0 - 1)) * chan + tl;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) cp_async16(stage + (size_t)(c * 4 + k) * T + tl, src + (size_t)c * chan + (size_t)k * T);
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) cp_async16(stage + (size_t)(c * 4 + k) * T + tl, src + (size_t)c * chan + (size_t)k * T);
+            }
         }
     };
 
+    if constexpr (BULK) {
+        if (tl == 0) mbar_init(mbar, 1);
+        __syncthreads();
+    }
+    unsigned phase = 0;
     pdl_wait();
     long long item = blockIdx.x;
     int mem = 0;
@@ -107,7 +127,12 @@ __global__ void __launch_bounds__(ENS_T, 2) k_len_ens(const UnitParams p, int n_
             const RotAngles<M> eangA = rot_angles_auto<M>(vec, p.vec_dv, (sa + sb) * p.cl[l0 - 1]);
             const RotAngles<M> eangB = rot_angles_auto<M>(vec, p.vec_dv, (sa + sb) * p.cl[l0 + 1]);
             // ---- psi of this task: staged by this very thread during the previous task ----
-            asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but F(task) has landed
+            if constexpr (BULK) {
+                mbar_wait(mbar, phase);
+                phase ^= 1u;
+            } else {
+                asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but F(task) has landed
+            }
             cplx QA[M], QB[M];
 #pragma unroll
             for (int k = 0; k < M; ++k) {
@@ -116,7 +141,7 @@ __global__ void __launch_bounds__(ENS_T, 2) k_len_ens(const UnitParams p, int n_
                 B[k] = stage[(size_t)(2 * 4 + k) * T + tl];
                 QB[k] = stage[(size_t)(3 * 4 + k) * T + tl];
             }
-            if (next_item < n_items) prefetch_psi(next_item, next_mem);
+            if (!BULK && next_item < n_items) prefetch_psi(next_item, next_mem);
             cp_async_commit();  // group P(next) (possibly empty)
             rotate_member<M>(A, QA, eangA);
             rotate_member<M>(B, QB, eangB);
@@ -131,12 +156,16 @@ __global__ void __launch_bounds__(ENS_T, 2) k_len_ens(const UnitParams p, int n_
             }
         }
         rotate_pair<M, false>(A, B, rang);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");  // F(task) has landed; P(next) may still be in flight
+        if constexpr (BULK) asm volatile("cp.async.wait_group 0;" ::: "memory");  // F(task) has landed
+        else asm volatile("cp.async.wait_group 1;" ::: "memory");                  // F(task) has landed; P(next) may still be in flight
         __syncwarp();  // a thread reads factors staged by itself and by its lane-pair partner only
         {
             cplx Z[8];
             pair_transpose_in(A, B, Z, odd);
-            cn8(Z, wsm + tl, T, tosm + pp, wprev, P8, Q8, tl, T, sm_scan, p.short_scan);
+            auto hook = [&]() {
+                if (BULK && next_item < n_items) prefetch_psi(next_item, next_mem);
+            };
+            cn8(Z, wsm + tl, T, tosm + pp, wprev, P8, Q8, tl, T, sm_scan, p.short_scan, hook);
             pair_transpose_out(Z, A, B, odd);  // its shuffles also order the pair's reads of wsm before the next task's staging
         }
         rotate_pair<M, false>(A, B, rang);

@@ -333,8 +333,14 @@ ION_DEVINL void pair_transpose_out(const cplx (&Z)[8], cplx (&X)[4], cplx (&Y)[4
 //   Pt, Qt: chunk multipliers (forward: e_{-1} e_0 .. e_6, backward: e_0 .. e_7)
 ION_DEVINL cplx e_of(double to, cplx w) { return c_make(to * w.y, -to * w.x); }  // -i * to * w
 
+struct NoHook {
+    ION_DEVINL void operator()() const {}
+};
+// `after_first_barrier`: called once every thread of the CTA has passed the forward scan's barrier (the ensemble kernel issues its
+// bulk prefetch there: by then all threads have read the staging buffer it overwrites)
+template <class Hook = NoHook>
 ION_DEVINL void cn8(cplx (&g)[8], const cplx *wcol, int T, const double *tocol, cplx wprev, cplx Pt, cplx Qt, int tid, int nthreads,
-                    cplx *sm, int reach)
+                    cplx *sm, int reach, Hook after_first_barrier = Hook())
 {
     const int TH = T >> 1;  // tocol[k * TH]: tau*off of row k of the chunk, k = 8: of the row before the chunk
 #define to_(k) tocol[(k) * TH]
@@ -343,6 +349,7 @@ ION_DEVINL void cn8(cplx (&g)[8], const cplx *wcol, int T, const double *tocol, 
 #pragma unroll
     for (int k = 1; k < 8; ++k) z = c_fma(e_of(to_(k - 1), wcol[(k - 1) * T]), z, g[k]);
     const cplx yin = affine_scan_strided_exclusive<true, 2>(Pt, z, sm, sm + 32, tid, nthreads, reach);
+    after_first_barrier();
     // forward, true inflow; u = w * y
     cplx u[8];
     cplx wk = wcol[0];
