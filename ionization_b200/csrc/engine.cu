@@ -290,7 +290,7 @@ size_t unit_smem_bytes(const ion_sim *s, int prog = -1)
 {
     size_t n = (256 + 4 * (size_t)s->Tc) * sizeof(cplx);
     const bool cn_pair = (prog == ion::PROG_ROT_CN_ROT || prog == ion::PROG_H2_CN_H2 || prog == ion::PROG_LEN_STEP || prog == ion::PROG_LEN_STEP_OBS || prog == ion::PROG_LEN_STEP_HALO || prog < 0);
-    if (cn_pair && s->M == 4 && s->tmax <= 512) n += 8 * (size_t)s->Tc * sizeof(cplx) + 9 * (size_t)(s->Tc / 2) * sizeof(double);
+    if (cn_pair && s->M == 4 && s->tmax <= 512) n += (8 * (size_t)s->Tc + 1) * sizeof(cplx) + (9 * (size_t)(s->Tc / 2) + 1) * sizeof(double) + 16;  // + pad, mbarrier
     return n;
 }
 

@@ -338,44 +338,49 @@ struct NoHook {
 };
 // `after_first_barrier`: called once every thread of the CTA has passed the forward scan's barrier (the ensemble kernel issues its
 // bulk prefetch there: by then all threads have read the staging buffer it overwrites)
-template <class Hook = NoHook>
+// NATURAL: the LU factors sit in shared memory as they sit in global memory -- one channel's four row planes [4][T], moved there by a
+// bulk copy -- and wcol points at the thread's column pair: row k of the chunk is plane k & 3, column k >> 2.  Otherwise (cp.async
+// staging, permuted on the way in): row k at wcol[k * T].
+template <class Hook = NoHook, bool NATURAL = false>
 ION_DEVINL void cn8(cplx (&g)[8], const cplx *wcol, int T, const double *tocol, cplx wprev, cplx Pt, cplx Qt, int tid, int nthreads,
                     cplx *sm, int reach, Hook after_first_barrier = Hook())
 {
     const int TH = T >> 1;  // tocol[k * TH]: tau*off of row k of the chunk, k = 8: of the row before the chunk
 #define to_(k) tocol[(k) * TH]
+#define wc_(k) wcol[NATURAL ? (((k) & 3) * T + ((k) >> 2)) : ((k) * T)]
     // forward, zero inflow
     cplx z = g[0];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) z = c_fma(e_of(to_(k - 1), wcol[(k - 1) * T]), z, g[k]);
+    for (int k = 1; k < 8; ++k) z = c_fma(e_of(to_(k - 1), wc_(k - 1)), z, g[k]);
     const cplx yin = affine_scan_strided_exclusive<true, 2>(Pt, z, sm, sm + 32, tid, nthreads, reach);
     after_first_barrier();
     // forward, true inflow; u = w * y
     cplx u[8];
-    cplx wk = wcol[0];
+    cplx wk = wc_(0);
     cplx y = c_fma(e_of(to_(8), wprev), yin, g[0]);
     u[0] = c_mul(wk, y);
 #pragma unroll
     for (int k = 1; k < 8; ++k) {
         const cplx e = e_of(to_(k - 1), wk);
-        wk = wcol[k * T];
+        wk = wc_(k);
         y = c_fma(e, y, g[k]);
         u[k] = c_mul(wk, y);
     }
     // backward, zero inflow
     z = u[7];
 #pragma unroll
-    for (int k = 6; k >= 0; --k) z = c_fma(e_of(to_(k), wcol[k * T]), z, u[k]);
+    for (int k = 6; k >= 0; --k) z = c_fma(e_of(to_(k), wc_(k)), z, u[k]);
     const cplx xin = affine_scan_strided_exclusive<false, 2>(Qt, z, sm + 64, sm + 96, tid, nthreads, reach);
     // backward, true inflow; out = 2 x - g
-    cplx x = c_fma(e_of(to_(7), wcol[7 * T]), xin, u[7]);
+    cplx x = c_fma(e_of(to_(7), wc_(7)), xin, u[7]);
     g[7] = c_make(fma(2.0, x.x, -g[7].x), fma(2.0, x.y, -g[7].y));
 #pragma unroll
     for (int k = 6; k >= 0; --k) {
-        x = c_fma(e_of(to_(k), wcol[k * T]), x, u[k]);
+        x = c_fma(e_of(to_(k), wc_(k)), x, u[k]);
         g[k] = c_make(fma(2.0, x.x, -g[k].x), fma(2.0, x.y, -g[k].y));
     }
 #undef to_
+#undef wc_
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -716,6 +721,9 @@ ION_DEVINL void line_cn_factors(CnFactors<M> &f, const cplx (&D)[M], const doubl
 // threads is below 1e-30 before it allows S > 1.  Halo results are discarded; only interior threads store.
 // The length-gauge programs (no r-pair bricks) take HALF-WARP halos (16 threads = 64 rows) when the product over any aligned
 // 16 threads is below 1e-18 -- two orders below the rounding of the values it multiplies: 224 interior threads of 256.
+#ifndef ION_LU_BULK
+#define ION_LU_BULK 1
+#endif
 template <int M, int PROG, int TMAX, bool SEG>
 #ifndef ION_PAIR_MINB
 #define ION_PAIR_MINB 1
@@ -826,8 +834,23 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
     ION_CK(0);
     cplx *obase = p.psi_out + ((size_t)b * p.L + l0) * chan;
     if constexpr (L2CN) if (pair) {
-        cplx *wsm = xs + 4 * Tc;                                  // [8][Tc]   LU factors, row k of the thread's chunk at wsm[k * Tc + tl]
-        double *tosm = reinterpret_cast<double *>(wsm + 8 * Tc);  // [9][Tc/2] tau*off of the chunk's rows (+ the row before it)
+        // LU factors of both channels.  One 512-thread CTA per pair: each channel's four row planes are one contiguous block in global memory,
+        // moved by the TMA engine (two cp.async.bulk issued by thread 0 at the very top, completion on an mbarrier) into [4][Tc] per
+        // channel; the upper channel is shifted by one element so that the two lanes of a lane pair -- even lane: lower channel, odd lane:
+        // upper channel, same columns -- read different banks.  r-segments: cp.async per thread, permuted to row k at wsm[k * Tc + tl].
+        constexpr bool LUB = !SEG && TMAX == 512 && (ION_LU_BULK != 0);  // (smaller CTAs: no gain, 500 x 50 measured 3 % slower)
+        cplx *wsm = xs + 4 * Tc;                                      // [8][Tc] (+ 1)
+        double *tosm = reinterpret_cast<double *>(wsm + 8 * Tc + 1);  // [9][Tc/2] tau*off of the chunk's rows (+ the row before it)
+        unsigned long long *lubar = reinterpret_cast<unsigned long long *>(tosm + 9 * (Tc >> 1) + ((9 * (Tc >> 1)) & 1));
+        if constexpr (LUB) {
+            if (tl == 0) {
+                mbar_init(lubar, 1);
+                mbar_expect_tx(lubar, (unsigned)(2 * chan * sizeof(cplx)));
+                bulk_g2s(wsm, p.w + (size_t)l0 * chan, (unsigned)(chan * sizeof(cplx)), lubar);
+                bulk_g2s(wsm + chan + 1, p.w + (size_t)(l0 + 1) * chan, (unsigned)(chan * sizeof(cplx)), lubar);
+            }
+            __syncthreads();  // the barrier is initialised before anybody waits on it
+        }
         const int pp = tl >> 1, TH = Tc >> 1;
         const bool odd = (tl & 1) != 0;
         // The small coefficient loads go FIRST: the 64 KB of LU factors of a 512-thread CTA keep the SM's load path busy for
@@ -865,7 +888,7 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
             czp = ok ? p.zprev[t] : 0.0;
             kap0 = sa * p.cl2[p.l_begin + l0];
         }
-        {   // coalesced reads of both channels' factors, permuted on the way into shared memory
+        if constexpr (!LUB) {   // coalesced reads of both channels' factors, permuted on the way into shared memory
             const cplx *w0 = p.w + (size_t)l0 * chan + t;
             cplx *dst = wsm + (size_t)(4 * (tl & 1)) * Tc + (tl & ~1);
 #pragma unroll
@@ -981,13 +1004,15 @@ __global__ void __launch_bounds__(TMAX, ((PROG == PROG_ROT || PROG == PROG_H2) &
         if (PROG == PROG_ROT_CN_ROT || LENSTEP) rotate_pair<M, false>(A, B, rang);
         else h2_pair<M>(A, B, pang, false, tl, Tc, xs);  // (oe, oo)
         ION_CK(3);
-        cp_async_wait_all();
-        __syncwarp();  // a thread reads factors staged by itself and by its lane-pair partner only (wprev comes from global memory)
+        if constexpr (LUB) mbar_wait(lubar, 0u);
+        else cp_async_wait_all();
+        __syncwarp();  // a thread reads factors (tau*off) staged by itself and by its lane-pair partner only (wprev comes from global memory)
         ION_CK(4);
         {
             cplx Z[8];
             pair_transpose_in(A, B, Z, odd);
-            cn8(Z, wsm + tl, Tc, tosm + pp, wprev, P8, Q8, tl, Tc, sm_scan, p.short_scan);
+            if constexpr (LUB) cn8<NoHook, true>(Z, wsm + (odd ? chan + 1 : 0) + 2 * pp, Tc, tosm + pp, wprev, P8, Q8, tl, Tc, sm_scan, p.short_scan);
+            else cn8(Z, wsm + tl, Tc, tosm + pp, wprev, P8, Q8, tl, Tc, sm_scan, p.short_scan);
             pair_transpose_out(Z, A, B, odd);
         }
         ION_CK(5);
