@@ -225,7 +225,7 @@ def test_peer_memory_halo_exchange_equals_unsharded_run_on_a_larger_mesh(kind):
     assert rel_err(g, g_ref) < 1e-12
 
 
-@pytest.mark.parametrize("shape", [(600, 64, 70), (600, 64, 150), (3000, 16, 70), (5000, 16, 70)])
+@pytest.mark.parametrize("shape", [(600, 64, 70), (600, 64, 150), (2000, 24, 70), (3000, 16, 70), (5000, 16, 70)])
 def test_halo_exchange_fused_into_the_length_gauge_step_equals_unsharded_run(shape):
     """PROG_LEN_STEP_HALO: the boundary CTAs of the folded step store their channel into the neighbour's memory and read their ghost
     partner from the slot the neighbour's previous launch filled -- no exchange kernel between fused steps.  The default for shards
