@@ -30,7 +30,10 @@ inline size_t ens_smem_bytes(int T) { return (256 + 8 * (size_t)T + 16 * (size_t
 // So (1) the CTAs in flight work on neighbouring pairs of the same members at the same time -- the read-only partner channels
 // hit L2 as before -- and (2) consecutive tasks of a CTA share their pair: the LU factors stay staged in shared memory and the
 // pair's scan multipliers hit L1 for ENS_MB - 1 of every ENS_MB tasks (one third less L2 -> SM traffic, no factor wait).
-constexpr int ENS_MB = 16;
+#ifndef ION_ENS_MB
+#define ION_ENS_MB 16
+#endif
+constexpr int ENS_MB = ION_ENS_MB;
 
 // BULK: the psi of the next task -- four consecutive channels, i.e. ONE contiguous 64 KB block in the row-interleaved layout -- is moved
 // by the TMA engine (cp.async.bulk, four 16 KB copies issued by one thread, completion on an mbarrier) instead of 16 cp.async per thread;
