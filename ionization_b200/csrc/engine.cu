@@ -147,6 +147,9 @@ struct ion_sim {
     // length gauge, fused observation: second set of the two buffers above -- the record of step n is assembled on the side branch while
     // the kernel of step n + 1 already fills the other set (obs_parity, ev_done as for the slab kernel)
     double *partial2 = nullptr, *ip_out2 = nullptr;
+    // velocity gauge, fused observation by STORING the observed state (slab.cuh: k_slab<true, true>): two buffers of psi's size, reduced by
+    // k_observe on the side branch
+    cplx *obs_psi[2] = {nullptr, nullptr};
     double *slab_partial = nullptr, *slab_ip = nullptr;  // per-slab partial sums of the fused observation (slab.cuh)
     unsigned *obs_counter = nullptr;                     // [batch] CTAs of k_slab_obs_assemble that are done
     // the record assembly of a fused observation runs on a side branch of the captured graph, so that the next step's kernels
@@ -201,6 +204,8 @@ struct ion_sim {
         if (psi2) cudaFree(psi2);
         if (slab_partial) cudaFree(slab_partial);
         if (slab_ip) cudaFree(slab_ip);
+        for (auto q : obs_psi)
+            if (q) cudaFree(q);
         if (partial2) cudaFree(partial2);
         if (ip_out2) cudaFree(ip_out2);
         if (obs_counter) cudaFree(obs_counter);
@@ -396,6 +401,7 @@ ion::UnitParams base_params(ion_sim *s)
 
 int launch_len_ens(ion_sim *s, const ion::UnitParams &p);
 int launch_observe_finish(ion_sim *s, uint32_t what, double *dev_out);
+int launch_observe(ion_sim *s, uint32_t what, double *dev_out);
 
 // a subset of the units of a launch: units sub_unit0 + k * sub_stride, k < sub_count (sub_count == 0: all units).  do_swap = false:
 // an out-of-place kernel leaves the buffer swap to the launch that covers the remaining units
@@ -782,6 +788,7 @@ int slab_prepare(ion_sim *s)
     if (int rc = ensure_second_buffer(s)) return rc;
     CUDA_TRY(cudaFuncSetAttribute(ion::k_slab<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 512 * (int)sizeof(cplx)));
     CUDA_TRY(cudaFuncSetAttribute(ion::k_slab<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 512 * (int)sizeof(cplx)));
+    CUDA_TRY(cudaFuncSetAttribute(ion::k_slab<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 512 * (int)sizeof(cplx)));
     s->slab_state = 1;
     return ION_OK;
 }
@@ -840,11 +847,36 @@ int launch_slab(ion_sim *s, const double *sa, const double *sb, uint32_t obs_wha
         o.n_states = (obs_what & ION_OBS_INNER_PRODUCTS) ? s->n_states : 0;
         for (int q = 0; q < o.n_radii; ++q) o.radii[q] = s->radii[q];
         o.what = obs_what;
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_slab<true>, p, o));
+        if (s->obs_psi[0] && s->obs_psi[1]) {
+            o.psi_n = s->obs_psi[k];
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_slab<true, true>, p, o));
+        } else {
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, ion::k_slab<true>, p, o));
+        }
     }
     prof_end(s);
     s->launch_count++;
     std::swap(s->psi, s->psi2);
+    if (obs_what && s->obs_psi[0] && s->obs_psi[1]) {
+        // side branch: k_observe + k_observe_finish on the stored state, while the main stream goes on with the next step
+        const int k = s->obs_parity;
+        s->obs_parity ^= 1;
+        CUDA_TRY(cudaEventRecord(s->ev_fork, s->stream));
+        CUDA_TRY(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
+        cudaStream_t main_stream = s->stream;
+        cplx *main_psi = s->psi;
+        const int g_lo = s->g_lo;
+        s->stream = s->side;
+        s->psi = s->obs_psi[k];
+        int rc = launch_observe(s, obs_what, obs_dst);
+        s->stream = main_stream;
+        s->psi = main_psi;
+        (void)g_lo;
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(s->ev_done[k], s->side));
+        s->side_pending[k] = true;
+        return ION_OK;
+    }
     if (obs_what) {
         // side branch: assemble the record while the main stream goes on with the next step
         const int k = s->obs_parity;
@@ -1387,6 +1419,19 @@ int run_impl(ion_sim *s, int64_t n_steps, const double *taus, const double *fiel
             CUDA_TRY(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
             for (auto &e : s->ev_done) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+    }
+    if (n_obs && s->slab_state == 1) {  // opt-in: the observed state is stored and reduced on the side branch (slab.cuh: STORE)
+        const char *env = std::getenv("ION_SLAB_OBS_STORE");
+        const size_t n = (size_t)s->batch * s->L * s->Rp;
+        // measured on C3: 47.1 us per observed step against 42.7 us with the in-kernel reductions (k_observe does not fit into the SM time the
+        // pair kernel's second wave leaves idle), so this is opt-in (ION_SLAB_OBS_STORE=1; it carries every observable k_observe knows)
+        if (env && env[0] == '1' && n * sizeof(cplx) <= ((size_t)256 << 20)) {
+            for (auto &q : s->obs_psi)
+                if (!q) {
+                    if (int rc = dev_alloc(&q, n)) return rc;
+                    CUDA_TRY(cudaMemsetAsync(q, 0, n * sizeof(cplx), s->stream));  // the padding rows are never written
+                }
         }
     }
     if (n_obs && s->slab_state == 1) {  // per-slab partial sums of the fused observation (slab.cuh)

@@ -66,6 +66,7 @@ struct SlabObs {
     double radii[ION_MAX_RADII];
     int n_radii, n_states;
     unsigned what;
+    cplx *psi_n;              // STORE: [batch][L][4][T] -- the observed state itself is written out (k_slab<true, true>)
 };
 
 // position of row r (>= 0) in the row-interleaved layout with M = 4
@@ -182,7 +183,11 @@ ION_DEVINL void slab_rot_upper(const cplx (&A)[4], cplx (&B)[4], const Trig (&an
 }
 
 // grid = (n_slabs * n_chunks, batch), block = NT (multiple of 32, NT >= G * (Qc + 2)); dynamic smem = 12 * NT cplx
-template <bool OBS>
+// STORE (with OBS; opt-in, ION_SLAB_OBS_STORE=1): instead of reducing in place, the kernel writes psi_n -- every interior point exactly
+// once -- into a second buffer and the stand-alone k_observe reduces it on a side branch of the stream / captured graph (every observable
+// k_observe knows rides along, <z> and <H0> included).  Measured slower on C3 (47.1 vs 42.7 us per observed step): k_observe's one-channel
+// CTAs do not fit into the SM time the 1.7-wave pair kernel of the next step leaves idle, and the main stream ends up waiting for them.
+template <bool OBS, bool STORE = false>
 __global__ void __launch_bounds__(512, 1) k_slab(const SlabParams p, const SlabObs o)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -325,7 +330,19 @@ __global__ void __launch_bounds__(512, 1) k_slab(const SlabParams p, const SlabO
 #pragma unroll
                     for (int j = 0; j < 4; ++j) X[c][j] = c_scale(X[c][j], 2.0 * mk[j]);
                 }
-                {   // ---- reductions over this thread's interior points; the G lanes of a quad are consecutive lanes ----
+                if constexpr (STORE) {   // ---- psi_n, interior points only (the stage-5 store pattern) ----
+                    if (q_ok && q >= q_int0 && q < q_int1) {
+                        cplx *nbase = o.psi_n + ((size_t)b * L + l0) * 4 * T;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int idx = 4 * g + j, r = r0 + j;
+                                if (l0 + c < L && idx >= 2 && idx < 4 * G - 2 && r >= 0 && r < p.R) st_c(nbase + (size_t)c * 4 * T + slab_pos(r, T), X[c][j]);
+                            }
+                        }
+                    }
+                } else {   // ---- reductions over this thread's interior points; the G lanes of a quad are consecutive lanes ----
                     const bool q_in = q_ok && q >= q_int0 && q < q_int1;
                     double rr[4];
                     bool in[4];
